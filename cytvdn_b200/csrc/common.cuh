@@ -1,0 +1,217 @@
+// common.cuh -- shared device/host helpers of libcytvdn_b200 (sm_100a only).
+//
+// Data layout (DESIGN.md "Data layout in HBM"): every array is the caller's C-contiguous
+// [N0,N1,N2,N3] block (3-D arrays are embedded as [N0,N1,1,N2]); axis 3 is unit stride.
+// A sweep walks the array in "strips": for each strip of TJ consecutive axis-1 indices,
+// for each axis-0 index i, the contiguous slab [i, strip, :, :] is cut into chunks of
+// kBlock*VW elements, one chunk per CTA iteration.  Consecutive tiles are therefore
+// consecutive in memory inside a slab, the axis-1 neighbour is one inner plane away and the
+// axis-0 neighbour TJ inner planes away, i.e. both stay L2 resident (126 MB) and are fetched
+// from HBM once.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cytvdn {
+
+constexpr int kBlock = 256;            // threads per CTA
+constexpr int kWarps = kBlock / 32;
+
+// ---- division of n < 2^31 by a runtime constant ------------------------------------------
+struct FastDiv {
+    uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    if (d == 0) d = 1;
+    f.d = d;
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    f.shr = s;
+    f.mul = (uint32_t)(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f)
+{
+    return (__umulhi(n, f.mul) + n) >> f.shr;
+}
+
+// ---- geometry and tiling of one launch ---------------------------------------------------
+struct Sweep {
+    int64_t st0, st1;          // element strides of axes 0 and 1
+    int32_t n0, n1, n2, n3;    // extents
+    int32_t n3v, mv;           // vectors per row / per inner plane (n2*n3v)
+    int32_t i0, j0, ni;        // sweep box: axis-0 origin/extent, axis-1 origin
+    int32_t tj, tl, nfull;     // strip width, width of the trailing partial strip (0: none), #full strips
+    int32_t cps_full, cps_last;// chunks per (i, strip) slab
+    int32_t tiles_full;        // ni * cps_full
+    int32_t ntiles;
+    int32_t oi0, oi1, oj0, oj1;// voxels with i in [oi0,oi1) and j in [oj0,oj1) enter the reductions
+    FastDiv d_tiles_full, d_cps_full, d_cps_last, d_mv, d_n3v;
+};
+
+struct Coord {                 // what one thread works on
+    int64_t e;                 // element offset of the first of its VW voxels
+    int32_t i, j, k, l0;
+    bool active, owned;
+};
+
+template <int VW>
+__device__ __forceinline__ Coord locate(const Sweep &S, int32_t t)
+{
+    int32_t s, ii, c, width;
+    const int32_t nfull_tiles = S.nfull * S.tiles_full;
+    if (t < nfull_tiles) {
+        s = (int32_t)fdiv((uint32_t)t, S.d_tiles_full);
+        const int32_t r = t - s * S.tiles_full;
+        ii = (int32_t)fdiv((uint32_t)r, S.d_cps_full);
+        c = r - ii * S.cps_full;
+        width = S.tj;
+    } else {
+        const int32_t r = t - nfull_tiles;
+        s = S.nfull;
+        ii = (int32_t)fdiv((uint32_t)r, S.d_cps_last);
+        c = r - ii * S.cps_last;
+        width = S.tl;
+    }
+    Coord p;
+    const int32_t jb = S.j0 + s * S.tj;
+    p.i = S.i0 + ii;
+    const int32_t len = width * S.mv;                 // vectors in this slab
+    const int32_t q = c * kBlock + (int32_t)threadIdx.x;
+    p.active = q < len;
+    const int32_t qq = p.active ? q : 0;
+    const int32_t jj = (int32_t)fdiv((uint32_t)qq, S.d_mv);
+    const int32_t m = qq - jj * S.mv;
+    p.k = (int32_t)fdiv((uint32_t)m, S.d_n3v);
+    p.l0 = (m - p.k * S.n3v) * VW;
+    p.j = jb + jj;
+    p.e = (int64_t)p.i * S.st0 + (int64_t)jb * S.st1 + (int64_t)qq * VW;
+    p.owned = p.active && p.i >= S.oi0 && p.i < S.oi1 && p.j >= S.oj0 && p.j < S.oj1;
+    return p;
+}
+
+// ---- vectors of VW elements (16 bytes when VW > 1) -------------------------------------------
+template <typename T, int VW> struct Raw;
+template <> struct Raw<float, 4>  { typedef float4  type; };
+template <> struct Raw<float, 1>  { typedef float   type; };
+template <> struct Raw<double, 2> { typedef double2 type; };
+template <> struct Raw<double, 1> { typedef double  type; };
+
+template <typename T, int VW>
+struct Vec {
+    T v[VW];
+};
+
+template <typename T, int VW>
+union VecU {
+    typename Raw<T, VW>::type r;
+    Vec<T, VW> v;
+    __device__ VecU() {}
+};
+
+// read-only data (never written by the running kernel): non-coherent path, default L2 policy
+template <typename T, int VW>
+__device__ __forceinline__ Vec<T, VW> ld_ro(const T *p)
+{
+    VecU<T, VW> u;
+    u.r = __ldg(reinterpret_cast<const typename Raw<T, VW>::type *>(p));
+    return u.v;
+}
+// streamed data (touched once per sweep): evict-first
+template <typename T, int VW>
+__device__ __forceinline__ Vec<T, VW> ld_stream(const T *p)
+{
+    VecU<T, VW> u;
+    u.r = __ldcs(reinterpret_cast<const typename Raw<T, VW>::type *>(p));
+    return u.v;
+}
+template <typename T, int VW>
+__device__ __forceinline__ void st_stream(T *p, const Vec<T, VW> &x)
+{
+    VecU<T, VW> u;
+    u.v = x;
+    __stcs(reinterpret_cast<typename Raw<T, VW>::type *>(p), u.r);
+}
+// data that is read and later re-read as a neighbour / written in place: default policy
+template <typename T, int VW>
+__device__ __forceinline__ Vec<T, VW> ld_plain(const T *p)
+{
+    VecU<T, VW> u;
+    u.r = *reinterpret_cast<const typename Raw<T, VW>::type *>(p);
+    return u.v;
+}
+template <typename T, int VW>
+__device__ __forceinline__ void st_plain(T *p, const Vec<T, VW> &x)
+{
+    VecU<T, VW> u;
+    u.v = x;
+    *reinterpret_cast<typename Raw<T, VW>::type *>(p) = u.r;
+}
+
+// ---- reductions: per-thread float64, warp shuffle, block smem, last-block fixed-order sum -------
+struct RedWork {
+    double *partials;     // [grid][NR]
+    unsigned *ticket;     // zero between launches
+    double *out;          // [NR] device
+};
+
+template <int NR>
+__device__ __forceinline__ void reduce_finish(double (&acc)[NR], const RedWork &W)
+{
+    __shared__ double sm[kWarps][NR];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double x = acc[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[warp][r] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            double x = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) x += sm[w][r];
+            W.partials[(size_t)blockIdx.x * NR + r] = x;
+        }
+        __threadfence();
+        const unsigned old = atomicAdd(W.ticket, 1u);
+        last = (old == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // the last CTA sums the per-CTA partials in a fixed order -> run-to-run deterministic
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double x = 0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kBlock)
+            x += __ldcg(&W.partials[(size_t)b * NR + r]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[warp][r] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            double x = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) x += sm[w][r];
+            W.out[r] = x;
+        }
+        *W.ticket = 0;
+    }
+}
+
+// |x| summed over one vector: float data is summed in float over the VW (<= 16) values a
+// thread handles per tile and promoted to double before it meets the running sum.
+__device__ __forceinline__ float  absval(float x)  { return fabsf(x); }
+__device__ __forceinline__ double absval(double x) { return fabs(x); }
+
+}  // namespace cytvdn

@@ -1,0 +1,738 @@
+// cytvdn_b200.cu -- C ABI of libcytvdn_b200.so (see include/cytvdn_b200.h) and the host side of
+// the launches: argument validation, sweep tiling, per-stream reduction workspaces and the
+// device-resident iteration loop that replaces the reference's Python host loops
+// (cyTVDN/cyTVDN.py:127-247, :350-435).
+#include "../../include/cytvdn_b200.h"
+#include "kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+using namespace cytvdn;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? CYTVDN_E_NOMEM : CYTVDN_E_CUDA,     \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- per (device, stream) reduction workspace ----------------------------------------------
+struct Workspace {
+    double *partials = nullptr;   // [kMaxGrid][4]
+    unsigned *ticket = nullptr;
+};
+constexpr int kMaxGrid = 148 * 16;
+std::mutex g_ws_mutex;
+std::map<std::pair<int, cudaStream_t>, Workspace> g_ws;
+
+int get_workspace(cudaStream_t st, Workspace *out)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    auto key = std::make_pair(dev, st);
+    auto it = g_ws.find(key);
+    if (it == g_ws.end()) {
+        Workspace w;
+        CUDA_TRY(cudaMalloc(&w.partials, sizeof(double) * 4 * kMaxGrid));
+        CUDA_TRY(cudaMalloc(&w.ticket, sizeof(unsigned) * 4));
+        CUDA_TRY(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned) * 4, st));
+        it = g_ws.emplace(key, w).first;
+    }
+    *out = it->second;
+    return CYTVDN_OK;
+}
+
+// ---- device properties / occupancy cache ------------------------------------------------------
+struct DevInfo {
+    int sms = 0;
+    size_t l2 = 0;
+};
+int dev_info(DevInfo *d)
+{
+    static std::mutex m;
+    static std::map<int, DevInfo> cache;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(m);
+    auto it = cache.find(dev);
+    if (it == cache.end()) {
+        DevInfo di;
+        int v = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        di.sms = v;
+        CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev));
+        di.l2 = (size_t)v;
+        it = cache.emplace(dev, di).first;
+    }
+    *d = it->second;
+    return CYTVDN_OK;
+}
+
+template <typename K>
+int grid_for(K kernel, int ntiles, int *grid)
+{
+    static std::mutex m;
+    static std::map<std::pair<int, const void *>, int> cache;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DevInfo di;
+    if (int rc = dev_info(&di)) return rc;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(m);
+        auto key = std::make_pair(dev, (const void *)kernel);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
+            if (per_sm < 1) per_sm = 1;
+            static const char *env = getenv("CYTVDN_CTAS_PER_SM");
+            if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
+            cache.emplace(key, per_sm);
+        } else {
+            per_sm = it->second;
+        }
+    }
+    int g = di.sms * per_sm;
+    if (g > kMaxGrid) g = kMaxGrid;
+    if (g > ntiles) g = ntiles;
+    if (g < 1) g = 1;
+    *grid = g;
+    return CYTVDN_OK;
+}
+
+// ---- geometry ----------------------------------------------------------------------------------
+struct Dims {
+    int ndim;
+    int64_t n[4];     // embedded 4-D extents ([N0,N1,1,N2] for 3-D)
+    int axmap[4];     // user axis -> embedded axis
+};
+
+int make_dims(int ndim, const int64_t *shape, Dims *D)
+{
+    if (ndim != 3 && ndim != 4) return fail(CYTVDN_E_INVALID, "ndim must be 3 or 4 (got %d)", ndim);
+    if (!shape) return fail(CYTVDN_E_INVALID, "shape is NULL");
+    for (int k = 0; k < ndim; ++k)
+        if (shape[k] < 1 || shape[k] > 0x7fffffff)
+            return fail(CYTVDN_E_INVALID, "shape[%d]=%lld out of range", k, (long long)shape[k]);
+    D->ndim = ndim;
+    if (ndim == 4) {
+        for (int k = 0; k < 4; ++k) { D->n[k] = shape[k]; D->axmap[k] = k; }
+    } else {
+        D->n[0] = shape[0]; D->n[1] = shape[1]; D->n[2] = 1; D->n[3] = shape[2];
+        D->axmap[0] = 0; D->axmap[1] = 1; D->axmap[2] = 3; D->axmap[3] = -1;
+    }
+    return CYTVDN_OK;
+}
+
+// bytes of L2 the strips of one sweep may occupy
+int64_t l2_budget(const cytvdn_step_opts *o)
+{
+    if (o && o->l2_budget_bytes > 0) return o->l2_budget_bytes;
+    const char *env = getenv("CYTVDN_L2_BUDGET_MB");      // read per call: tests shrink it to force strips
+    if (env && atof(env) > 0) return (int64_t)(atof(env) * 1048576.0);
+    return 24ll << 20;
+}
+
+// footprint_arrays: number of distinct arrays whose lines live in L2 during the sweep
+int make_sweep(const Dims &D, int vw, size_t elem, const cytvdn_step_opts *o, int footprint_arrays, Sweep *S)
+{
+    memset(S, 0, sizeof *S);
+    S->n0 = (int32_t)D.n[0]; S->n1 = (int32_t)D.n[1]; S->n2 = (int32_t)D.n[2]; S->n3 = (int32_t)D.n[3];
+    S->st1 = D.n[2] * D.n[3];
+    S->st0 = D.n[1] * S->st1;
+    if (S->st1 / vw > 0x3fffffff) return fail(CYTVDN_E_INVALID, "inner plane too large");
+    S->n3v = (int32_t)(D.n[3] / vw);
+    S->mv = (int32_t)(S->st1 / vw);
+    int64_t lo[2] = {0, 0}, hi[2] = {D.n[0], D.n[1]}, olo[2] = {0, 0}, ohi[2] = {D.n[0], D.n[1]};
+    if (o) {
+        for (int k = 0; k < 2; ++k) {
+            lo[k] = o->box_lo[k];
+            if (o->box_hi[k] > 0) hi[k] = o->box_hi[k];
+            olo[k] = o->own_lo[k];
+            if (o->own_hi[k] > 0) ohi[k] = o->own_hi[k];
+            if (lo[k] < 0 || hi[k] > D.n[k] || lo[k] > hi[k])
+                return fail(CYTVDN_E_INVALID, "opts box on axis %d is [%lld,%lld) for extent %lld", k,
+                            (long long)lo[k], (long long)hi[k], (long long)D.n[k]);
+        }
+    }
+    S->i0 = (int32_t)lo[0]; S->ni = (int32_t)(hi[0] - lo[0]);
+    S->j0 = (int32_t)lo[1];
+    const int64_t nj = hi[1] - lo[1];
+    S->oi0 = (int32_t)olo[0]; S->oi1 = (int32_t)ohi[0]; S->oj0 = (int32_t)olo[1]; S->oj1 = (int32_t)ohi[1];
+
+    // strip width: keep TJ inner planes of every array of the sweep inside the L2 budget
+    const int64_t plane_bytes = S->st1 * (int64_t)elem * footprint_arrays;
+    int64_t tjmax = l2_budget(o) / (plane_bytes > 0 ? plane_bytes : 1);
+    const int64_t cap = (1ll << 30) / (S->mv > 0 ? S->mv : 1);       // slab vector count must fit int32
+    if (tjmax > cap) tjmax = cap;
+    if (tjmax < 1) tjmax = 1;
+    int64_t tj = nj;
+    if (nj > tjmax) {
+        const int64_t nstrips = (nj + tjmax - 1) / tjmax;
+        tj = (nj + nstrips - 1) / nstrips;
+    }
+    if (tj < 1) tj = 1;
+    S->tj = (int32_t)tj;
+    S->nfull = (int32_t)(nj / tj);
+    S->tl = (int32_t)(nj - (int64_t)S->nfull * tj);
+    S->cps_full = (int32_t)((tj * S->mv + kBlock - 1) / kBlock);
+    S->cps_last = (int32_t)(((int64_t)S->tl * S->mv + kBlock - 1) / kBlock);
+    const int64_t tiles_full = (int64_t)S->ni * S->cps_full;
+    const int64_t ntiles = tiles_full * S->nfull + (int64_t)S->ni * S->cps_last;
+    if (tiles_full > 0x7fffffff || ntiles > 0x7fffffff) return fail(CYTVDN_E_INVALID, "array too large for one sweep");
+    S->tiles_full = (int32_t)tiles_full;
+    S->ntiles = (int32_t)ntiles;
+    S->d_tiles_full = make_fastdiv((uint32_t)(S->tiles_full > 0 ? S->tiles_full : 1));
+    S->d_cps_full = make_fastdiv((uint32_t)(S->cps_full > 0 ? S->cps_full : 1));
+    S->d_cps_last = make_fastdiv((uint32_t)(S->cps_last > 0 ? S->cps_last : 1));
+    S->d_mv = make_fastdiv((uint32_t)S->mv);
+    S->d_n3v = make_fastdiv((uint32_t)S->n3v);
+    return CYTVDN_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T> constexpr int vec_width() { return 16 / (int)sizeof(T); }
+
+// ---- half-step A -------------------------------------------------------------------------------
+template <typename T, int VW, bool FISTA>
+int launch_acc_mode(int mode, const AccParams<T> &P, cudaStream_t st)
+{
+    int grid = 1;
+    if (P.S.ntiles <= 0) return CYTVDN_OK;
+    switch (mode) {
+    case ACC_ALL4: {
+        auto k = tv_accumulator_kernel<T, VW, FISTA, ACC_ALL4>;
+        if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
+        k<<<grid, kBlock, 0, st>>>(P);
+        break;
+    }
+    case ACC_ALL3: {
+        auto k = tv_accumulator_kernel<T, VW, FISTA, ACC_ALL3>;
+        if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
+        k<<<grid, kBlock, 0, st>>>(P);
+        break;
+    }
+    default: {
+        auto k = tv_accumulator_kernel<T, VW, FISTA, ACC_GEN>;
+        if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
+        k<<<grid, kBlock, 0, st>>>(P);
+        break;
+    }
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return CYTVDN_OK;
+}
+
+struct AccCall {
+    Dims D;
+    const void *a;
+    void *b[4];          // embedded axis order
+    void *d[4];
+    double clip[4];
+    int bc[4];
+    bool fista;
+    double tk;
+    int mode;
+    int axmask;
+    int iso_p, iso_q, iso_mask;
+    double *norm_dev;
+    const cytvdn_step_opts *opts;
+    cudaStream_t st;
+};
+
+template <typename T>
+int run_acc(const AccCall &c)
+{
+    AccParams<T> P;
+    memset(&P, 0, sizeof P);
+    bool vec = (c.D.n[3] % vec_width<T>() == 0) && aligned16(c.a);
+    int nax = 0;
+    for (int k = 0; k < 4; ++k) {
+        const bool on = c.mode == ACC_ALL4 ? true : c.mode == ACC_ALL3 ? (k != 2) : ((c.axmask >> k) & 1);
+        P.clip[k] = (T)c.clip[k];
+        P.bc[k] = c.bc[k];
+        if (!on) continue;
+        ++nax;
+        if (!c.b[k]) return fail(CYTVDN_E_INVALID, "accumulator for axis slot %d is NULL", k);
+        if (c.fista && !c.d[k]) return fail(CYTVDN_E_INVALID, "FISTA auxiliary for axis slot %d is NULL", k);
+        vec = vec && aligned16(c.b[k]) && (!c.fista || aligned16(c.d[k]));
+        P.b[k] = (T *)c.b[k];
+        P.d[k] = (T *)c.d[k];
+    }
+    const int vw = vec ? vec_width<T>() : 1;
+    if (int rc = make_sweep(c.D, vw, sizeof(T), c.opts, 1 + nax * (c.fista ? 2 : 1), &P.S)) return rc;
+    P.u = (const T *)c.a;
+    P.tk = (T)c.tk;
+    P.axmask = c.axmask;
+    P.iso_p = c.iso_p; P.iso_q = c.iso_q; P.iso_mask = c.iso_mask;
+    Workspace w;
+    if (int rc = get_workspace(c.st, &w)) return rc;
+    P.W.partials = w.partials; P.W.ticket = w.ticket; P.W.out = c.norm_dev;
+    if (P.S.ntiles <= 0) {       // empty box: the sum is 0
+        CUDA_TRY(cudaMemsetAsync(c.norm_dev, 0, sizeof(double), c.st));
+        return CYTVDN_OK;
+    }
+    if (vec) {
+        return c.fista ? launch_acc_mode<T, vec_width<T>(), true>(c.mode, P, c.st)
+                       : launch_acc_mode<T, vec_width<T>(), false>(c.mode, P, c.st);
+    }
+    return c.fista ? launch_acc_mode<T, 1, true>(c.mode, P, c.st) : launch_acc_mode<T, 1, false>(c.mode, P, c.st);
+}
+
+int check_common(int dtype, const void *a, const double *out_dev)
+{
+    if (dtype != CYTVDN_F32 && dtype != CYTVDN_F64) return fail(CYTVDN_E_INVALID, "dtype must be CYTVDN_F32 or CYTVDN_F64");
+    if (!a) return fail(CYTVDN_E_INVALID, "input array pointer is NULL");
+    if (!out_dev) return fail(CYTVDN_E_INVALID, "reduction output pointer is NULL");
+    return CYTVDN_OK;
+}
+
+// ---- half-step B -------------------------------------------------------------------------------
+template <typename T>
+int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const void *const *b,
+            const double *w, int zero_wrap, double *sums_dev, const cytvdn_step_opts *opts, cudaStream_t st)
+{
+    DcuParams<T> P;
+    memset(&P, 0, sizeof P);
+    bool vec = (D.n[3] % vec_width<T>() == 0) && aligned16(orig) && aligned16(uin) && aligned16(uout);
+    for (int k = 0; k < D.ndim; ++k) {
+        const int s = D.axmap[k];
+        if (!b[k]) return fail(CYTVDN_E_INVALID, "b[%d] is NULL", k);
+        vec = vec && aligned16(b[k]);
+        P.b[s] = (const T *)b[k];
+        P.w[s] = (T)w[k];
+        if ((zero_wrap >> k) & 1) P.zero_wrap |= 1 << s;
+    }
+    const int vw = vec ? vec_width<T>() : 1;
+    if (int rc = make_sweep(D, vw, sizeof(T), opts, 2 + D.ndim, &P.S)) return rc;
+    P.f = (const T *)orig; P.uin = (const T *)uin; P.uout = (T *)uout;
+    Workspace ws;
+    if (int rc = get_workspace(st, &ws)) return rc;
+    P.W.partials = ws.partials; P.W.ticket = ws.ticket; P.W.out = sums_dev;
+    if (P.S.ntiles <= 0) {
+        CUDA_TRY(cudaMemsetAsync(sums_dev, 0, 2 * sizeof(double), st));
+        return CYTVDN_OK;
+    }
+    int grid = 1;
+#define LAUNCH_DCU(VWV, AX2V)                                                          \
+    do {                                                                               \
+        auto k = tv_datacube_kernel<T, VWV, AX2V>;                                     \
+        if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;                        \
+        k<<<grid, kBlock, 0, st>>>(P);                                                 \
+    } while (0)
+    if (vec) { if (D.ndim == 4) LAUNCH_DCU(vec_width<T>(), true); else LAUNCH_DCU(vec_width<T>(), false); }
+    else     { if (D.ndim == 4) LAUNCH_DCU(1, true); else LAUNCH_DCU(1, false); }
+#undef LAUNCH_DCU
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return CYTVDN_OK;
+}
+
+template <typename T>
+int run_sse(int64_t n, const void *a, const void *b, double *out, cudaStream_t st)
+{
+    Workspace ws;
+    if (int rc = get_workspace(st, &ws)) return rc;
+    RedWork W{ws.partials, ws.ticket, out};
+    if (n <= 0) { CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double), st)); return CYTVDN_OK; }
+    int grid = 1;
+    auto k = tv_sse_kernel<T>;
+    const int64_t blocks = (n + kBlock - 1) / kBlock;
+    if (int rc = grid_for(k, (int)(blocks > 0x7fffffff ? 0x7fffffff : blocks), &grid)) return rc;
+    k<<<grid, kBlock, 0, st>>>((const T *)a, (const T *)b, n, W);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return CYTVDN_OK;
+}
+
+bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int cytvdn_version(void) { return CYTVDN_VERSION; }
+const char *cytvdn_last_error(void) { return g_err.c_str(); }
+int64_t cytvdn_launch_count(void) { return g_launches.load(); }
+
+int cytvdn_device_count(int *count)
+{
+    if (!count) return fail(CYTVDN_E_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return CYTVDN_OK;
+}
+
+int cytvdn_accumulator_update(int ndim, const int64_t *shape, int dtype, const void *a, void *b, void *d,
+                              double tk, int ax, double clip, int bc_mode, double *norm_dev,
+                              const cytvdn_step_opts *opts, void *stream)
+{
+    AccCall c;
+    memset(&c, 0, sizeof c);
+    if (int rc = make_dims(ndim, shape, &c.D)) return rc;
+    if (int rc = check_common(dtype, a, norm_dev)) return rc;
+    if (ax < 0 || ax >= ndim) return fail(CYTVDN_E_INVALID, "ax=%d out of range for ndim=%d", ax, ndim);
+    if (bc_mode < 0 || bc_mode > 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1 or 2");
+    if (bc_mode == 1 && shape[ax] < 2) return fail(CYTVDN_E_INVALID, "mirror boundary needs extent >= 2 on axis %d", ax);
+    if (!b) return fail(CYTVDN_E_INVALID, "b is NULL");
+    const int s = c.D.axmap[ax];
+    c.a = a; c.b[s] = b; c.d[s] = d; c.clip[s] = clip; c.bc[s] = bc_mode;
+    c.fista = d != nullptr; c.tk = tk; c.mode = ACC_GEN; c.axmask = 1 << s;
+    c.iso_p = c.iso_q = -1; c.norm_dev = norm_dev; c.opts = opts; c.st = (cudaStream_t)stream;
+    return dtype == CYTVDN_F32 ? run_acc<float>(c) : run_acc<double>(c);
+}
+
+int cytvdn_iso_accumulator_update(const int64_t *shape, int dtype, const void *a, void *b1, void *b2, void *d1,
+                                  void *d2, double tk, int ax1, int ax2, double clip, double *norm_dev,
+                                  const cytvdn_step_opts *opts, void *stream)
+{
+    AccCall c;
+    memset(&c, 0, sizeof c);
+    if (int rc = make_dims(4, shape, &c.D)) return rc;
+    if (int rc = check_common(dtype, a, norm_dev)) return rc;
+    if (ax1 < 0 || ax1 > 3 || ax2 < 0 || ax2 > 3 || ax1 == ax2)
+        return fail(CYTVDN_E_INVALID, "ax1/ax2 must be two different axes in 0..3 (got %d, %d)", ax1, ax2);
+    if (!b1 || !b2) return fail(CYTVDN_E_INVALID, "b1/b2 is NULL");
+    if ((d1 == nullptr) != (d2 == nullptr)) return fail(CYTVDN_E_INVALID, "d1 and d2 must both be given or both be NULL");
+    c.a = a; c.b[ax1] = b1; c.b[ax2] = b2; c.d[ax1] = d1; c.d[ax2] = d2;
+    for (int k = 0; k < 4; ++k) c.clip[k] = clip;     // the pair shares one threshold (clip[0] in the kernel)
+    c.bc[ax1] = c.bc[ax2] = 2;
+    c.fista = d1 != nullptr; c.tk = tk; c.mode = ACC_GEN; c.axmask = (1 << ax1) | (1 << ax2);
+    c.iso_p = ax1; c.iso_q = ax2; c.norm_dev = norm_dev; c.opts = opts; c.st = (cudaStream_t)stream;
+    return dtype == CYTVDN_F32 ? run_acc<float>(c) : run_acc<double>(c);
+}
+
+int cytvdn_accumulator_update_all(int ndim, const int64_t *shape, int dtype, const void *a, void *const *b,
+                                  void *const *d, double tk, const double *clip, int iso_R, int iso_Q,
+                                  int bc_mode, double *norm_dev, const cytvdn_step_opts *opts, void *stream)
+{
+    AccCall c;
+    memset(&c, 0, sizeof c);
+    if (int rc = make_dims(ndim, shape, &c.D)) return rc;
+    if (int rc = check_common(dtype, a, norm_dev)) return rc;
+    if (!b || !clip) return fail(CYTVDN_E_INVALID, "b / clip is NULL");
+    if (bc_mode < 0 || bc_mode > 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1 or 2");
+    if (ndim == 3 && (iso_R || iso_Q)) return fail(CYTVDN_E_INVALID, "half-isotropic update exists for 4-D only");
+    for (int k = 0; k < ndim; ++k) {
+        const int s = c.D.axmap[k];
+        c.b[s] = b[k]; c.d[s] = d ? d[k] : nullptr; c.clip[s] = clip[k];
+        const bool iso = (k < 2 && iso_R) || (k >= 2 && iso_Q);
+        c.bc[s] = iso ? 2 : bc_mode;                       // iso_* kernels know Jia-Zhao only
+        if (c.bc[s] == 1 && shape[k] < 2) return fail(CYTVDN_E_INVALID, "mirror boundary needs extent >= 2 on axis %d", k);
+    }
+    c.a = a; c.fista = d != nullptr; c.tk = tk;
+    c.mode = ndim == 4 ? ACC_ALL4 : ACC_ALL3;
+    c.axmask = ndim == 4 ? 15 : 11;
+    c.iso_p = c.iso_q = -1; c.iso_mask = (iso_R ? 1 : 0) | (iso_Q ? 2 : 0);
+    c.norm_dev = norm_dev; c.opts = opts; c.st = (cudaStream_t)stream;
+    return dtype == CYTVDN_F32 ? run_acc<float>(c) : run_acc<double>(c);
+}
+
+int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void *orig, const void *recon_in,
+                           void *recon_out, const void *const *b, const double *lambda_mu, int bc_mode,
+                           double *sums_dev, const cytvdn_step_opts *opts, void *stream)
+{
+    Dims D;
+    if (int rc = make_dims(ndim, shape, &D)) return rc;
+    if (int rc = check_common(dtype, orig, sums_dev)) return rc;
+    if (!recon_in || !recon_out || !b || !lambda_mu) return fail(CYTVDN_E_INVALID, "recon / b / lambda_mu is NULL");
+    if (bc_mode == 1)
+        return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=1 (mirror) is undefined behaviour in the reference's "
+                                          "datacube_update (utils.pyx:117-120) and is not implemented");
+    if (bc_mode != 0 && bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
+    const int zw = opts ? opts->zero_wrap_mask : 0;
+    return dtype == CYTVDN_F32
+               ? run_dcu<float>(D, orig, recon_in, recon_out, b, lambda_mu, zw, sums_dev, opts, (cudaStream_t)stream)
+               : run_dcu<double>(D, orig, recon_in, recon_out, b, lambda_mu, zw, sums_dev, opts, (cudaStream_t)stream);
+}
+
+int cytvdn_sum_square_error(int64_t n, int dtype, const void *a, const void *b, double *sse_dev, void *stream)
+{
+    if (int rc = check_common(dtype, a, sse_dev)) return rc;
+    if (!b) return fail(CYTVDN_E_INVALID, "b is NULL");
+    if (n < 0) return fail(CYTVDN_E_INVALID, "n < 0");
+    return dtype == CYTVDN_F32 ? run_sse<float>(n, a, b, sse_dev, (cudaStream_t)stream)
+                               : run_sse<double>(n, a, b, sse_dev, (cudaStream_t)stream);
+}
+
+int cytvdn_synth_counts(const int64_t *gshape, int64_t offset0, int64_t lshape0, int dtype,
+                        const float *scan_mod_dev, const float *templ_dev, double counts, uint64_t seed,
+                        void *out_dev, void *stream)
+{
+    if (!gshape || !scan_mod_dev || !templ_dev || !out_dev) return fail(CYTVDN_E_INVALID, "NULL argument");
+    if (dtype != CYTVDN_F32 && dtype != CYTVDN_F64) return fail(CYTVDN_E_INVALID, "bad dtype");
+    if (offset0 < 0 || lshape0 < 0 || offset0 + lshape0 > gshape[0]) return fail(CYTVDN_E_INVALID, "bad block range");
+    const int64_t m = gshape[2] * gshape[3];
+    const int64_t st0 = gshape[1] * m;
+    if (m > 0x7fffffff) return fail(CYTVDN_E_INVALID, "inner plane too large");
+    const int64_t nloc = lshape0 * st0;
+    if (nloc == 0) return CYTVDN_OK;
+    DevInfo di;
+    if (int rc = dev_info(&di)) return rc;
+    int64_t blocks = (nloc + kBlock - 1) / kBlock;
+    const int grid = (int)(blocks < (int64_t)di.sms * 8 ? blocks : (int64_t)di.sms * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CYTVDN_F32)
+        tv_synth_kernel<float><<<grid, kBlock, 0, st>>>((float *)out_dev, nloc, offset0 * st0, m,
+                                                       scan_mod_dev, templ_dev, (float)counts, seed);
+    else
+        tv_synth_kernel<double><<<grid, kBlock, 0, st>>>((double *)out_dev, nloc, offset0 * st0, m,
+                                                        scan_mod_dev, templ_dev, (float)counts, seed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return CYTVDN_OK;
+}
+
+// ---- the device-resident loop -------------------------------------------------------------------
+static int validate_params(const cytvdn_denoise_params *p, Dims *D)
+{
+    if (!p) return fail(CYTVDN_E_INVALID, "params is NULL");
+    if (int rc = make_dims(p->ndim, p->shape, D)) return rc;
+    if (p->dtype != CYTVDN_F32 && p->dtype != CYTVDN_F64) return fail(CYTVDN_E_INVALID, "bad dtype");
+    if (p->iters_fista < 0 || p->iters_plain < 0) return fail(CYTVDN_E_INVALID, "negative iteration count");
+    if (p->bc_mode == 1)
+        return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=1 (mirror) is undefined behaviour in the reference's "
+                                          "datacube_update (utils.pyx:117-120) and is not implemented");
+    if (p->bc_mode != 0 && p->bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
+    if (p->ndim == 3 && (p->isotropic_R || p->isotropic_Q))
+        return fail(CYTVDN_E_INVALID, "half-isotropic update exists for 4-D only");
+    return CYTVDN_OK;
+}
+
+int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *p, int data_on_device, int recon_on_device,
+                                   int64_t *bytes)
+{
+    Dims D;
+    if (int rc = validate_params(p, &D)) return rc;
+    if (!bytes) return fail(CYTVDN_E_INVALID, "bytes is NULL");
+    const int64_t nb = D.n[0] * D.n[1] * D.n[2] * D.n[3] * (p->dtype == CYTVDN_F32 ? 4 : 8);
+    int64_t arrays = p->ndim + (p->iters_fista > 0 ? p->ndim : 0);
+    if (!data_on_device) arrays += 1;
+    if (!recon_on_device) arrays += 1;
+    *bytes = arrays * nb;
+    return CYTVDN_OK;
+}
+
+namespace {
+struct DevBuf {      // frees on scope exit
+    std::vector<void *> ptrs;
+    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    int alloc(void **p, size_t bytes)
+    {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CYTVDN_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+        ptrs.push_back(*p);
+        return CYTVDN_OK;
+    }
+};
+}  // namespace
+
+int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon, const void *reference_data,
+                   double *bnorm, double *delta, double *mse, int32_t *iters_done, double *timing_ms)
+{
+    Dims D;
+    if (int rc = validate_params(p, &D)) return rc;
+    if (!data || !recon) return fail(CYTVDN_E_INVALID, "data / recon is NULL");
+    const int nF = p->iters_fista, nU = p->iters_plain, nIt = nF + nU;
+    if (nIt > 0 && (!bnorm || !delta)) return fail(CYTVDN_E_INVALID, "bnorm / delta is NULL");
+    if (reference_data && !mse) return fail(CYTVDN_E_INVALID, "mse is NULL but reference_data was given");
+    const size_t elem = p->dtype == CYTVDN_F32 ? 4 : 8;
+    const int64_t nvox = D.n[0] * D.n[1] * D.n[2] * D.n[3];
+    const size_t nb = (size_t)nvox * elem;
+    const int nd = p->ndim;
+
+    const bool data_dev = is_device_ptr(data), recon_dev = is_device_ptr(recon);
+    const bool ref_dev = reference_data ? is_device_ptr(reference_data) : false;
+    int prev_dev = -1;
+    CUDA_TRY(cudaGetDevice(&prev_dev));
+    if (!data_dev && p->device >= 0) CUDA_TRY(cudaSetDevice(p->device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+    cudaStream_t st = (cudaStream_t)p->stream;
+
+    cudaEvent_t ev[4];
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    struct EvFree { cudaEvent_t *e; ~EvFree() { for (int k = 0; k < 4; ++k) cudaEventDestroy(e[k]); } } evfree{ev};
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+
+    DevBuf pool;
+    void *b[4] = {0, 0, 0, 0}, *d[4] = {0, 0, 0, 0};
+    void *orig_d = nullptr, *recon_d = nullptr, *ref_d = nullptr;
+    double *sums_d = nullptr;
+    if (data_dev) orig_d = const_cast<void *>(data);
+    else { if (int rc = pool.alloc(&orig_d, nb)) return rc; CUDA_TRY(cudaMemcpyAsync(orig_d, data, nb, cudaMemcpyHostToDevice, st)); }
+    if (recon_dev) recon_d = recon;
+    else if (int rc = pool.alloc(&recon_d, nb)) return rc;
+    if (reference_data) {
+        if (ref_dev) ref_d = const_cast<void *>(reference_data);
+        else { if (int rc = pool.alloc(&ref_d, nb)) return rc; CUDA_TRY(cudaMemcpyAsync(ref_d, reference_data, nb, cudaMemcpyHostToDevice, st)); }
+    }
+    for (int k = 0; k < nd && nIt > 0; ++k) {
+        if (int rc = pool.alloc(&b[k], nb)) return rc;
+        CUDA_TRY(cudaMemsetAsync(b[k], 0, nb, st));
+        if (nF > 0) {
+            if (int rc = pool.alloc(&d[k], nb)) return rc;
+            CUDA_TRY(cudaMemsetAsync(d[k], 0, nb, st));
+        }
+    }
+    // per iteration: [0] sum|b|, [1] sum|delta|, [2] sum|old|, [3] sse ; slot nIt holds MSE[0]
+    const size_t nsums = (size_t)(nIt + 1) * 4;
+    if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
+    CUDA_TRY(cudaMemsetAsync(sums_d, 0, nsums * sizeof(double), st));
+    std::vector<double> sums_h(nsums, 0.0);
+    double *pinned = nullptr;
+    if (p->use_stopping) CUDA_TRY(cudaMallocHost(&pinned, 4 * sizeof(double)));
+    struct PinFree { double *p; ~PinFree() { if (p) cudaFreeHost(p); } } pinfree{pinned};
+
+    if (reference_data)
+        if (int rc = cytvdn_sum_square_error(nvox, p->dtype, orig_d, ref_d, sums_d + (size_t)nIt * 4 + 3, st)) return rc;
+
+    CUDA_TRY(cudaEventRecord(ev[1], st));
+    // iteration 0 reads the reconstruction straight from the input (recon = datacube.copy(),
+    // cyTVDN.py:145) and writes recon_d, which saves the device-to-device copy.
+    const void *u_cur = orig_d;
+    double tk = 1.0;
+    int done[2] = {0, 0};
+    std::vector<char> ran(nIt > 0 ? nIt : 1, 0);
+    for (int phase = 0; phase < 2; ++phase) {
+        const int n = phase == 0 ? nF : nU;
+        for (int it = 0; it < n; ++it) {
+            const int i = phase == 0 ? it : nF + it;
+            double tkr = 0.0;
+            if (phase == 0) {                                   // cyTVDN.py:154-156
+                const double tk_new = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
+                tkr = (tk - 1.0) / tk_new;
+                tk = tk_new;
+            }
+            double *s = sums_d + (size_t)i * 4;
+            if (int rc = cytvdn_accumulator_update_all(nd, p->shape, p->dtype, u_cur, b, phase == 0 ? d : nullptr, tkr,
+                                                       p->clip, p->isotropic_R, p->isotropic_Q, p->bc_mode, s, nullptr, st))
+                return rc;
+            if (int rc = cytvdn_datacube_update(nd, p->shape, p->dtype, orig_d, u_cur, recon_d, b, p->lambda_mu,
+                                                p->bc_mode, s + 1, nullptr, st))
+                return rc;
+            u_cur = recon_d;
+            if (reference_data)
+                if (int rc = cytvdn_sum_square_error(nvox, p->dtype, ref_d, recon_d, s + 3, st)) return rc;
+            ran[i] = 1;
+            ++done[phase];
+            if (p->use_stopping) {                              // cyTVDN.py:189-194 / :236-242
+                CUDA_TRY(cudaMemcpyAsync(pinned, s, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                const double dl = pinned[1] / pinned[2];
+                const double dl_t = p->dtype == CYTVDN_F32 ? (double)(float)dl : dl;   // stored in the array dtype
+                if (dl_t < p->stopping_relative_change) break;
+            }
+        }
+    }
+    if (nIt == 0 || u_cur == orig_d)
+        CUDA_TRY(cudaMemcpyAsync(recon_d, orig_d, nb, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaEventRecord(ev[2], st));
+
+    if (!recon_dev) CUDA_TRY(cudaMemcpyAsync(recon, recon_d, nb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(sums_h.data(), sums_d, nsums * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < nIt; ++i) {
+        bnorm[i] = ran[i] ? sums_h[(size_t)i * 4 + 0] : 0.0;
+        delta[i] = ran[i] ? sums_h[(size_t)i * 4 + 1] / sums_h[(size_t)i * 4 + 2] : 0.0;
+        if (mse) mse[i + 1] = ran[i] ? sums_h[(size_t)i * 4 + 3] : 0.0;
+    }
+    if (mse) mse[0] = sums_h[(size_t)nIt * 4 + 3];
+    if (iters_done) { iters_done[0] = done[0]; iters_done[1] = done[1]; }
+    for (void *q : pool.ptrs) cudaFree(q);
+    pool.ptrs.clear();
+    CUDA_TRY(cudaEventRecord(ev[3], st));
+    CUDA_TRY(cudaEventSynchronize(ev[3]));
+    if (timing_ms) {
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, ev[0], ev[1])); timing_ms[0] = t;
+        CUDA_TRY(cudaEventElapsedTime(&t, ev[1], ev[2])); timing_ms[1] = t;
+        CUDA_TRY(cudaEventElapsedTime(&t, ev[2], ev[3])); timing_ms[2] = t;
+    }
+    return CYTVDN_OK;
+}
+
+// ---- small CUDA helpers -----------------------------------------------------------------------
+int cytvdn_malloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return fail(CYTVDN_E_INVALID, "bad argument");
+    *ptr = nullptr;
+    if (bytes == 0) return CYTVDN_OK;
+    CUDA_TRY(cudaMalloc(ptr, (size_t)bytes));
+    return CYTVDN_OK;
+}
+int cytvdn_free(void *ptr) { if (ptr) CUDA_TRY(cudaFree(ptr)); return CYTVDN_OK; }
+int cytvdn_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return fail(CYTVDN_E_INVALID, "bad argument");
+    *ptr = nullptr;
+    if (bytes == 0) return CYTVDN_OK;
+    CUDA_TRY(cudaMallocHost(ptr, (size_t)bytes));
+    return CYTVDN_OK;
+}
+int cytvdn_host_free(void *ptr) { if (ptr) CUDA_TRY(cudaFreeHost(ptr)); return CYTVDN_OK; }
+int cytvdn_memcpy(void *dst, const void *src, int64_t bytes, void *stream)
+{
+    if (bytes <= 0) return CYTVDN_OK;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return CYTVDN_OK;
+}
+int cytvdn_memset(void *dst, int value, int64_t bytes, void *stream)
+{
+    if (bytes <= 0) return CYTVDN_OK;
+    CUDA_TRY(cudaMemsetAsync(dst, value, (size_t)bytes, (cudaStream_t)stream));
+    return CYTVDN_OK;
+}
+int cytvdn_stream_synchronize(void *stream) { CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream)); return CYTVDN_OK; }
+int cytvdn_set_device(int device) { CUDA_TRY(cudaSetDevice(device)); return CYTVDN_OK; }
+int cytvdn_get_device(int *device) { if (!device) return fail(CYTVDN_E_INVALID, "NULL"); CUDA_TRY(cudaGetDevice(device)); return CYTVDN_OK; }
+int cytvdn_mem_info(int64_t *free_bytes, int64_t *total_bytes)
+{
+    size_t f = 0, t = 0;
+    CUDA_TRY(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return CYTVDN_OK;
+}
+
+}  // extern "C"

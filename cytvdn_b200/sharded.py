@@ -1,0 +1,392 @@
+"""Scan-axis sharding of the 4-D TV iteration over several GPUs (one process per GPU).
+
+Re-expression of the reference's MPI scheme (`cyTVDN/mpi.py:130-210` partition, `:314-438`
+iteration + exchange; description `README.md:104-120`) with torch.distributed / NCCL:
+
+* tiles over the scan axes 0/1 on a ``wx x wy`` grid, each tile stores its owned block plus ONE
+  overlap plane towards every existing neighbour (`mpi.py:165-196`);
+* every rank runs the same two fused kernels on its local block;
+* after half-step A the accumulator of a split axis is shifted right: the sender's LAST OWNED
+  plane replaces the receiver's plane 0; after half-step B the reconstruction is shifted left:
+  the sender's FIRST OWNED plane replaces the receiver's last plane.
+
+Deviations from `mpi.py`, all required for the sharded result to equal the single-process one
+(verified there against the compiled reference):
+  - `mpi.py:325,344,408,414` send the overlap planes (``acc[-1]``, ``recon[0]``); the owned planes
+    ``acc[-2]`` / ``recon[1]`` are sent here;
+  - a tile on the global upper edge that has a left neighbour must not wrap its last plane onto the
+    received plane 0 (`utils.pyx:98-99`): the kernel gets ``zero_wrap_mask``;
+  - FISTA is supported (the reference stops at "haven't done FISTA yet", `mpi.py:310-311`): only the
+    accumulators travel, never the auxiliaries;
+  - ``b_norm`` / ``delta`` are produced: sums over OWNED voxels, all-reduced (3 doubles / iteration).
+Only ``BC_mode=2`` exists in sharded mode, as in `mpi.py:84`.
+
+Default layout on NVSwitch: 1-D over axis 0 (contiguous halo planes, two neighbours); the halo planes
+are computed first and travel on a side stream while the interior is computed.  The reference's 2-D
+``(wx, wy)`` heuristic (`mpi.py:131-150`) is available as ``grid="mpi"`` (no overlap of compute and
+exchange in that mode).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# partition (pure host logic, exercised on CPU by tests/test_sharded_cpu.py)
+# ------------------------------------------------------------------------------------------------
+def mpi_grid(size: Sequence[int], nworkers: int) -> Tuple[int, int]:
+    """The reference's choice of (wx, wy): minimise the total edge length, first minimum wins
+    (`mpi.py:131-150`)."""
+    best, best_edges = None, None
+    for wx in range(1, nworkers + 1):
+        if nworkers % wx:
+            continue
+        wy = nworkers // wx
+        edges = (nworkers - 1) * (2 * math.ceil(size[0] / wx) + 2 * math.ceil(size[1] / wy))
+        if best_edges is None or edges < best_edges:
+            best, best_edges = (wx, wy), edges
+    return best
+
+
+@dataclass(frozen=True)
+class HaloOp:
+    """One plane transfer: local plane ``send_index`` of ``array`` along ``axis`` goes to rank ``peer``
+    (``kind='send'``) or plane ``recv_index`` is filled from rank ``peer`` (``kind='recv'``)."""
+    kind: str
+    array: str          # "b0", "b1" or "recon"
+    axis: int
+    index: int
+    peer: int
+
+
+class ShardPlan:
+    """Where one rank's block sits in the global array and what it exchanges."""
+
+    def __init__(self, gshape: Sequence[int], world: int, rank: int, grid=None):
+        gshape = tuple(int(v) for v in gshape)
+        assert len(gshape) == 4, "sharding exists for 4-D datacubes only (mpi.py:252-255)"
+        if grid is None:
+            grid = (world, 1)
+        elif grid == "mpi":
+            grid = mpi_grid(gshape[:2], world)
+        wx, wy = int(grid[0]), int(grid[1])
+        assert wx * wy == world, f"grid {grid} does not match world size {world}"
+        self.gshape, self.world, self.rank, self.grid = gshape, world, rank, (wx, wy)
+        self.tile = (rank // wy, rank % wy)                       # np.unravel_index(rank, (wx, wy)), mpi.py:156
+        n = [math.ceil(gshape[0] / wx), math.ceil(gshape[1] / wy)]   # mpi.py:161-162
+        self.valid, self.read, self.has_lo, self.has_hi = [], [], [], []
+        for k in range(2):
+            t, w = self.tile[k], (wx, wy)[k]
+            lo, hi = t * n[k], min((t + 1) * n[k], gshape[k])     # mpi.py:165-170
+            if hi - lo < 1:
+                raise ValueError(f"axis {k}: extent {gshape[k]} cannot be split over {w} tiles of {n[k]} planes "
+                                 f"(tile {t} would be empty)")
+            has_lo, has_hi = t > 0, t < w - 1                      # mpi.py:183-187
+            self.valid.append((lo, hi))
+            self.read.append((lo - 1 if has_lo else lo, hi + 1 if has_hi else hi))   # mpi.py:173-180
+            self.has_lo.append(has_lo)
+            self.has_hi.append(has_hi)
+        self.local_shape = (self.read[0][1] - self.read[0][0], self.read[1][1] - self.read[1][0]) + gshape[2:]
+        # owned block in local coordinates (mpi.py:195-196)
+        self.own_lo = [1 if self.has_lo[k] else 0 for k in range(2)]
+        self.own_hi = [self.local_shape[k] - (1 if self.has_hi[k] else 0) for k in range(2)]
+
+    # neighbour ranks (mpi.py:199-210)
+    def peer(self, axis: int, step: int) -> int:
+        t = list(self.tile)
+        t[axis] += step
+        return t[0] * self.grid[1] + t[1]
+
+    @property
+    def owned_local(self):
+        return (slice(self.own_lo[0], self.own_hi[0]), slice(self.own_lo[1], self.own_hi[1]))
+
+    @property
+    def owned_global(self):
+        return (slice(*self.valid[0]), slice(*self.valid[1]))
+
+    @property
+    def read_global(self):
+        return (slice(*self.read[0]), slice(*self.read[1]))
+
+    @property
+    def owned_voxels(self) -> int:
+        return ((self.valid[0][1] - self.valid[0][0]) * (self.valid[1][1] - self.valid[1][0])
+                * self.gshape[2] * self.gshape[3])
+
+    @property
+    def zero_wrap_mask(self) -> int:
+        """Axes on which this tile ends at the global upper edge but holds a received plane 0."""
+        return sum(1 << k for k in range(2) if self.has_lo[k] and not self.has_hi[k])
+
+    def after_a(self) -> List[HaloOp]:
+        """Accumulators shift right (corrected plane indices)."""
+        ops = []
+        for k in range(2):
+            if self.has_hi[k]:
+                ops.append(HaloOp("send", f"b{k}", k, self.local_shape[k] - 2, self.peer(k, +1)))
+            if self.has_lo[k]:
+                ops.append(HaloOp("recv", f"b{k}", k, 0, self.peer(k, -1)))
+        return ops
+
+    def after_b(self) -> List[HaloOp]:
+        """Reconstruction shifts left."""
+        ops = []
+        for k in range(2):
+            if self.has_lo[k]:
+                ops.append(HaloOp("send", "recon", k, 1, self.peer(k, -1)))
+            if self.has_hi[k]:
+                ops.append(HaloOp("recv", "recon", k, self.local_shape[k] - 1, self.peer(k, +1)))
+        return ops
+
+    # sweep boxes (axis-0 ranges) for the overlapped 1-D schedule
+    def a_boxes(self):
+        """(halo-first, rest) axis-0 ranges of half-step A.  Halo-first: the plane that is sent and
+        the plane that will be overwritten by the receive."""
+        n = self.local_shape[0]
+        first = []
+        if self.has_lo[0]:
+            first.append((0, 1))
+        if self.has_hi[0]:
+            first.append((n - 2, n - 1))
+        rest = _complement(n, first)
+        return first, rest
+
+    def b_boxes(self):
+        """Half-step B: the first owned plane (sent left) goes first; the last plane is skipped when
+        it is an overlap plane (it is received)."""
+        n = self.local_shape[0]
+        first = [(1, 2)] if self.has_lo[0] else []
+        skip = [(n - 1, n)] if self.has_hi[0] else []
+        rest = _complement(n, first + skip)
+        return first, rest
+
+    def describe(self) -> str:
+        return (f"rank {self.rank}/{self.world} tile {self.tile} of grid {self.grid}: owns "
+                f"[{self.valid[0][0]}:{self.valid[0][1]}, {self.valid[1][0]}:{self.valid[1][1]}], "
+                f"stores {self.local_shape}")
+
+
+def _complement(n, boxes):
+    out, cur = [], 0
+    for lo, hi in sorted(boxes):
+        if lo > cur:
+            out.append((cur, lo))
+        cur = max(cur, hi)
+    if cur < n:
+        out.append((cur, n))
+    return out
+
+
+def plane(t, axis: int, index: int):
+    """View of one plane of a 4-D tensor / array."""
+    return t[index] if axis == 0 else t[:, index]
+
+
+def fista_ratio(tk: float):
+    """cyTVDN.py:154-156 (float64 on the host)."""
+    tk_new = (1.0 + math.sqrt(1.0 + 4.0 * tk * tk)) / 2.0
+    return (tk - 1.0) / tk_new, tk_new
+
+
+def halo_exchange(ops: List[HaloOp], arrays: dict, group=None):
+    """Post the plane transfers of one half-step with torch.distributed P2P (NCCL on GPUs, gloo in the
+    CPU tests).  Returns (works, unpack) -- call ``unpack()`` after the works completed to scatter
+    planes that had to be staged (axis-1 planes are strided)."""
+    import torch
+    import torch.distributed as dist
+    p2p, staged = [], []
+    for op in ops:
+        view = plane(arrays[op.array], op.axis, op.index)
+        if op.kind == "send":
+            buf = view if view.is_contiguous() else view.contiguous()
+            p2p.append(dist.P2POp(dist.isend, buf, op.peer, group))
+        else:
+            if view.is_contiguous():
+                p2p.append(dist.P2POp(dist.irecv, view, op.peer, group))
+            else:
+                buf = torch.empty_like(view, memory_format=torch.contiguous_format)
+                staged.append((view, buf))
+                p2p.append(dist.P2POp(dist.irecv, buf, op.peer, group))
+    works = dist.batch_isend_irecv(p2p) if p2p else []
+
+    def unpack():
+        for view, buf in staged:
+            view.copy_(buf)
+    return works, unpack
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA worker: one rank's state and launches
+# ------------------------------------------------------------------------------------------------
+class CudaShard:
+    """Device state of one rank (local block with overlap planes) and its kernel launches."""
+
+    SLOTS = 16          # doubles of reduction scratch per iteration
+
+    def __init__(self, plan: ShardPlan, shard, mu, lam=None, fista=True, n_iter=1):
+        import torch
+        from . import _lib
+        self.torch, self._lib, self.lib = torch, _lib, _lib.load()
+        _lib.require_gpu()
+        assert tuple(shard.shape) == tuple(plan.local_shape), (tuple(shard.shape), plan.local_shape)
+        assert shard.is_cuda and shard.is_contiguous() and shard.dtype in (torch.float32, torch.float64)
+        self.plan, self.orig, self.fista = plan, shard, fista
+        dt = np.float32 if shard.dtype == torch.float32 else np.float64
+        mu = np.asarray(mu, dtype=dt)
+        lam = (mu * 1.0 / 32.0) if lam is None else np.asarray(lam, dtype=dt)      # cyTVDN.py:67-68
+        self.clip = (C.c_double * 4)(*[float(v) for v in (1.0 / lam)])
+        self.w = (C.c_double * 4)(*[float(v) for v in (lam / mu).astype(dt)])
+        self.code = 0 if dt == np.float32 else 1
+        self.recon = shard.clone()
+        self.b = [torch.zeros_like(shard) for _ in range(4)]
+        self.d = [torch.zeros_like(shard) for _ in range(4)] if fista else None
+        self.bp = (C.c_void_p * 4)(*[t.data_ptr() for t in self.b])
+        self.dp = (C.c_void_p * 4)(*[t.data_ptr() for t in self.d]) if fista else None
+        self.sh = (C.c_int64 * 4)(*plan.local_shape)
+        self.sums = torch.zeros((max(n_iter, 1), self.SLOTS), dtype=torch.float64, device=shard.device)
+        self.arrays = {"b0": self.b[0], "b1": self.b[1], "recon": self.recon}
+        self.launches = 0
+
+    def _opts(self, box0=None):
+        o = self._lib.StepOpts()
+        n0 = self.plan.local_shape[0]
+        o.box_lo[0], o.box_hi[0] = (0, n0) if box0 is None else box0
+        o.box_lo[1], o.box_hi[1] = 0, 0
+        for k in range(2):
+            o.own_lo[k], o.own_hi[k] = self.plan.own_lo[k], self.plan.own_hi[k]
+        o.zero_wrap_mask = self.plan.zero_wrap_mask
+        return o
+
+    def half_step_a(self, it: int, slot: int, tk_ratio: float, fista: bool, box0=None):
+        st = self.torch.cuda.current_stream(self.orig.device).cuda_stream
+        out = self.sums.data_ptr() + 8 * (it * self.SLOTS + slot)
+        o = self._opts(box0)
+        self._lib.check(self.lib.cytvdn_accumulator_update_all(
+            4, self.sh, self.code, self.recon.data_ptr(), self.bp, self.dp if fista else None, float(tk_ratio),
+            self.clip, 0, 0, 2, out, C.byref(o), st))
+        self.launches += 1
+
+    def half_step_b(self, it: int, slot: int, box0=None):
+        st = self.torch.cuda.current_stream(self.orig.device).cuda_stream
+        out = self.sums.data_ptr() + 8 * (it * self.SLOTS + slot)
+        o = self._opts(box0)
+        self._lib.check(self.lib.cytvdn_datacube_update(
+            4, self.sh, self.code, self.orig.data_ptr(), self.recon.data_ptr(), self.recon.data_ptr(), self.bp,
+            self.w, 2, out, C.byref(o), st))
+        self.launches += 1
+
+    # slot layout per iteration: A launches 0..3 (1 double each), B launches 4.. (2 doubles each)
+    def local_sums(self):
+        s = self.sums
+        return self.torch.stack([s[:, 0:4].sum(1), s[:, 4:16:2].sum(1), s[:, 5:16:2].sum(1)], dim=1)
+
+
+def _run_iteration_overlapped(sh: CudaShard, it, tkr, fista, group, comm_stream):
+    """1-D (axis-0) schedule: halo planes first, exchange on ``comm_stream`` under the interior sweep."""
+    torch = sh.torch
+    main = torch.cuda.current_stream(sh.orig.device)
+    plan = sh.plan
+    for phase in ("a", "b"):
+        first, rest = plan.a_boxes() if phase == "a" else plan.b_boxes()
+        ops = plan.after_a() if phase == "a" else plan.after_b()
+        slot = 0 if phase == "a" else 4
+        step = 1 if phase == "a" else 2
+        for box in first:
+            (sh.half_step_a(it, slot, tkr, fista, box) if phase == "a" else sh.half_step_b(it, slot, box))
+            slot += step
+        if ops:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev)
+                works, unpack = halo_exchange(ops, sh.arrays, group)
+                for w_ in works:
+                    w_.wait()
+                unpack()
+        for box in rest:
+            (sh.half_step_a(it, slot, tkr, fista, box) if phase == "a" else sh.half_step_b(it, slot, box))
+            slot += step
+        if ops:
+            main.wait_stream(comm_stream)
+
+
+def _run_iteration_simple(sh: CudaShard, it, tkr, fista, group):
+    """Any grid: full sweep, then exchange (what `mpi.py` does, minus its barriers)."""
+    for phase in ("a", "b"):
+        if phase == "a":
+            sh.half_step_a(it, 0, tkr, fista)
+        else:
+            sh.half_step_b(it, 4)
+        ops = sh.plan.after_a() if phase == "a" else sh.plan.after_b()
+        if ops:
+            works, unpack = halo_exchange(ops, sh.arrays, group)
+            for w_ in works:
+                w_.wait()
+            unpack()
+
+
+def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_change=None, *, plan: ShardPlan,
+                      group=None, lam=None, overlap=True, return_state=False):
+    """Sharded counterpart of ``denoise4D`` -- call it on every rank of the process group.
+
+    ``shard``: this rank's block INCLUDING its overlap planes (``plan.read_global`` of the global
+    array), a contiguous CUDA tensor.  Returns ``(recon_local, b_norm, delta_recon)`` where
+    ``recon_local[plan.owned_local]`` is this rank's part of the result and the two 1-D arrays are the
+    global values (owned-voxel sums, all-reduced).  ``iterations`` may be ``[n_FISTA, n_plain]``.
+    """
+    import torch
+    import torch.distributed as dist
+    unaccelerated = not FISTA
+    if type(iterations) in (list, tuple):
+        FISTA, unaccelerated = True, True
+        nF, nU = int(iterations[0]), int(iterations[1])
+    else:
+        nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
+    n = nF + nU
+    world = plan.world
+    sh = CudaShard(plan, shard, mu, lam, fista=nF > 0, n_iter=n)
+    one_d = plan.grid[1] == 1
+    comm_stream = torch.cuda.Stream(device=shard.device) if (overlap and one_d and world > 1) else None
+    ran = np.zeros(n, dtype=bool)
+    tk = 1.0
+    glob = torch.zeros((max(n, 1), 3), dtype=torch.float64, device=shard.device)
+    for phase, count in ((0, nF), (1, nU)):
+        for j in range(count):
+            it = j if phase == 0 else nF + j
+            tkr = 0.0
+            if phase == 0:
+                tkr, tk = fista_ratio(tk)
+            if comm_stream is not None:
+                _run_iteration_overlapped(sh, it, tkr, phase == 0, group, comm_stream)
+            else:
+                _run_iteration_simple(sh, it, tkr, phase == 0, group)
+            ran[it] = True
+            if stopping_relative_change is not None:          # needs the global delta now
+                s = sh.local_sums()[it].clone()
+                if world > 1:
+                    dist.all_reduce(s, group=group)
+                glob[it] = s
+                dl = float(s[1] / s[2])
+                if shard.dtype == torch.float32:
+                    dl = float(np.float32(dl))
+                if dl < stopping_relative_change:
+                    break
+    if stopping_relative_change is None and n > 0:
+        glob = sh.local_sums().clone()
+        if world > 1:
+            dist.all_reduce(glob, group=group)
+    g = glob.cpu().numpy()
+    dt = np.float32 if shard.dtype == torch.float32 else np.float64
+    with np.errstate(all="ignore"):
+        b_norm = np.where(ran, g[:n, 0], 0.0).astype(dt)
+        delta = np.where(ran, g[:n, 1] / g[:n, 2], 0.0).astype(dt)
+    torch.cuda.current_stream(shard.device).synchronize()
+    if return_state:
+        return sh.recon, b_norm, delta, sh
+    return sh.recon, b_norm, delta

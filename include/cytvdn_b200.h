@@ -1,0 +1,199 @@
+/*
+ * cytvdn_b200.h -- C ABI of libcytvdn_b200.so: the TV-denoising hot path of cyTVDN
+ * (tv.denoise3D / tv.denoise4D) as hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference has no C ABI: its
+ * native interface is three CPython extension modules taking typed memoryviews.  Each entry
+ * point below names the reference function it replaces (file:line under /root/reference).
+ * Plain pointers and sizes only; no torch / numpy types.  All functions return 0 on success
+ * or a CYTVDN_E_* code; cytvdn_last_error() gives the message of the calling thread's last
+ * failure.  Nothing here ever falls back to the CPU.
+ *
+ * Conventions
+ *  - Arrays are C-contiguous, dtype CYTVDN_F32 or CYTVDN_F64, ndim 3 or 4, `shape` has ndim
+ *    entries.  All arrays of one call share dtype and shape (the reference raises
+ *    "Buffer dtype mismatch" otherwise).
+ *  - Step-level functions take DEVICE pointers and are stream-ordered (asynchronous); their
+ *    reductions are written as doubles to DEVICE memory (`*_dev`), never accumulated.
+ *    Scalars that the reference casts to the array dtype at the call (clip, tk, lambda_mu)
+ *    are passed as double and rounded to the array dtype inside, exactly like the reference.
+ *  - bc_mode: 0 periodic, 1 mirror, 2 Jia-Zhao (anisotropic.pyx:20-24).  Mirror is only
+ *    defined for the accumulator update; the reference's reconstruction update with
+ *    bc_mode 1 reads out of bounds (utils.pyx:117-120) and is rejected here.
+ *  - Per-voxel arithmetic is bit-identical to the reference (separately rounded mul/add,
+ *    IEEE division, comparison-based clip); only the reductions differ: they are
+ *    accumulated in float64 (the reference's array-dtype sums are inaccurate).
+ */
+#ifndef CYTVDN_B200_H
+#define CYTVDN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYTVDN_VERSION 100          /* 0.1.0 */
+
+#define CYTVDN_F32 0
+#define CYTVDN_F64 1
+
+#define CYTVDN_OK            0
+#define CYTVDN_E_INVALID     1      /* bad argument (message says which) */
+#define CYTVDN_E_CUDA        2      /* CUDA runtime error */
+#define CYTVDN_E_NOMEM       3      /* device allocation failed */
+#define CYTVDN_E_UNSUPPORTED 4      /* e.g. bc_mode 1 in the reconstruction update */
+
+int         cytvdn_version(void);
+const char *cytvdn_last_error(void);
+/* number of CUDA devices; 0 (and CYTVDN_OK) on a machine without a GPU */
+int         cytvdn_device_count(int *count);
+
+/*
+ * Optional extras for the step functions (NULL = whole array, reference semantics).
+ * They exist for the scan-axis sharding that replaces cyTVDN/mpi.py:155-210,314-438:
+ *  box_*   : half-open range of axis-0 / axis-1 indices swept by this launch (lets the
+ *            caller launch halo planes first and the interior on another stream);
+ *            box_hi[k] <= 0 means "up to the extent".
+ *  own_*   : range whose voxels enter the reductions (overlap planes excluded);
+ *            own_hi[k] <= 0 means "up to the extent".
+ *  zero_wrap_mask (reconstruction update only): bit k set -> the forward neighbour of the
+ *            last index on axis k is taken as 0 instead of reading index 0 (tile on the
+ *            global upper edge that holds a received plane at index 0).
+ *  l2_budget_bytes : working-set budget that sizes the axis-1 strips of the sweep
+ *            (0 = library default).
+ */
+typedef struct cytvdn_step_opts {
+    int64_t box_lo[2];
+    int64_t box_hi[2];
+    int64_t own_lo[2];
+    int64_t own_hi[2];
+    int32_t zero_wrap_mask;
+    int32_t reserved;
+    int64_t l2_budget_bytes;
+} cytvdn_step_opts;
+
+/*
+ * Half-step A, one axis.  Replaces
+ *   accumulator_update_4D        anisotropic.pyx:17-84     (ndim 4, d == NULL)
+ *   accumulator_update_4D_FISTA  anisotropic.pyx:89-164    (ndim 4, d != NULL)
+ *   accumulator_update_3D        anisotropic.pyx:169-237   (ndim 3, d == NULL)
+ *   accumulator_update_3D_FISTA  anisotropic.pyx:243-317   (ndim 3, d != NULL)
+ * b (and d) are updated in place; *norm_dev = sum |b_new| (their return value).
+ */
+int cytvdn_accumulator_update(int ndim, const int64_t *shape, int dtype,
+                              const void *a, void *b, void *d, double tk, int ax, double clip,
+                              int bc_mode, double *norm_dev, const cytvdn_step_opts *opts,
+                              void *stream);
+
+/*
+ * Half-step A for an axis pair with joint 2-norm shrink (4-D, Jia-Zhao boundary only).  Replaces
+ *   iso_accumulator_update_4D        halfisotropic.pyx:17-97     (d1 == d2 == NULL)
+ *   iso_accumulator_update_4D_FISTA  halfisotropic.pyx:102-188
+ * with race-free semantics (the reference shares scratch between OpenMP threads).
+ */
+int cytvdn_iso_accumulator_update(const int64_t *shape, int dtype, const void *a,
+                                  void *b1, void *b2, void *d1, void *d2, double tk,
+                                  int ax1, int ax2, double clip, double *norm_dev,
+                                  const cytvdn_step_opts *opts, void *stream);
+
+/*
+ * Half-step A for ALL axes in one pass over `a` (what denoise3D/4D use).  Equivalent to the
+ * ndim calls of cyTVDN.py:159-180 (4-D; :378-386 3-D): b[k]/d[k]/clip[k] belong to axis k;
+ * iso_R / iso_Q select the half-isotropic update for the pairs (0,1) / (2,3) with
+ * clip[0] / clip[2] as in cyTVDN.py:160-162,171-173.  d == NULL -> unaccelerated.
+ * *norm_dev = sum over all axes of sum |b_new| (= b_norm[i] of the reference).
+ */
+int cytvdn_accumulator_update_all(int ndim, const int64_t *shape, int dtype, const void *a,
+                                  void *const *b, void *const *d, double tk,
+                                  const double *clip, int iso_R, int iso_Q, int bc_mode,
+                                  double *norm_dev, const cytvdn_step_opts *opts, void *stream);
+
+/*
+ * Half-step B.  Replaces datacube_update_4D utils.pyx:54-125 and datacube_update_3D
+ * utils.pyx:131-199 (bc_mode 0 and 2 share one path there, :85/:163).
+ * recon_out[x] = orig[x] - sum_k lambda_mu[k] * (b[k][x] - b[k][x + e_k mod N_k]),
+ * summed left to right.  recon_in may equal recon_out (the reference updates in place).
+ * sums_dev[0] = sum |recon_out - recon_in|, sums_dev[1] = sum |recon_in|; the reference
+ * returns their ratio.
+ */
+int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void *orig,
+                           const void *recon_in, void *recon_out, const void *const *b,
+                           const double *lambda_mu, int bc_mode, double *sums_dev,
+                           const cytvdn_step_opts *opts, void *stream);
+
+/* sum (a-b)^2 over n elements.  Replaces sum_square_error_4D utils.pyx:14-30, _3D :35-49. */
+int cytvdn_sum_square_error(int64_t n, int dtype, const void *a, const void *b,
+                            double *sse_dev, void *stream);
+
+/*
+ * The whole iteration loop, device resident.  Replaces the host loops of
+ * denoise4D cyTVDN.py:127-247 and denoise3D cyTVDN.py:350-435.
+ */
+typedef struct cytvdn_denoise_params {
+    int32_t ndim;               /* 3 or 4 */
+    int32_t dtype;              /* CYTVDN_F32 / CYTVDN_F64 */
+    int64_t shape[4];
+    int32_t iters_fista;        /* FISTA iterations first ... */
+    int32_t iters_plain;        /* ... then unaccelerated ones (cyTVDN.py:98-108) */
+    int32_t isotropic_R;        /* 4-D only */
+    int32_t isotropic_Q;        /* 4-D only */
+    int32_t bc_mode;            /* 0 or 2 */
+    int32_t use_stopping;       /* stop a phase when delta < stopping_relative_change */
+    double  stopping_relative_change;
+    double  clip[4];            /* lambdaInv = 1/lam  (cyTVDN.py:77) */
+    double  lambda_mu[4];       /* lam/mu             (cyTVDN.py:78) */
+    int32_t device;             /* device to run on when `data` is a host pointer; -1 = current */
+    int32_t reserved;
+    void   *stream;             /* NULL = default stream */
+} cytvdn_denoise_params;
+
+/*
+ * data, recon, reference_data: host or device pointers (detected); data is never modified;
+ * recon receives the result.  bnorm / delta: HOST arrays of iters_fista + iters_plain doubles
+ * (entries of iterations that did not run stay 0, like the reference's trailing zeros);
+ * mse: HOST array of that length + 1, or NULL when reference_data is NULL.
+ * iters_done[0], iters_done[1]: FISTA / unaccelerated iterations actually executed.
+ * timing_ms (may be NULL): [0] allocation + host->device, [1] iteration loop (CUDA events),
+ * [2] device->host + free.
+ * The call is synchronous.
+ */
+int cytvdn_denoise(const cytvdn_denoise_params *params, const void *data, void *recon,
+                   const void *reference_data, double *bnorm, double *delta, double *mse,
+                   int32_t *iters_done, double *timing_ms);
+
+/* Device working set of cytvdn_denoise in bytes (GPU analogue of check_memory, cyTVDN.py:438). */
+int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *params, int data_on_device,
+                                   int recon_on_device, int64_t *bytes);
+
+/*
+ * Deterministic synthetic 4D-STEM-like counts for benchmarks and sharded parity runs
+ * (SURVEY.md section 8d): out[x] = max(0, rint(c + sqrt(c) * z(x))) with
+ * c = counts * scan_mod[i,j] * templ[k,l] + 0.02 * counts and z an approximately normal
+ * deviate derived from a 64-bit hash of (seed, GLOBAL linear index), so any sharding of the
+ * global array yields the same values.  `out` is the local block starting at axis-0 index
+ * `offset0` of a global array with shape `gshape`; `lshape0` planes are written.
+ * scan_mod: device float[gshape0*gshape1]; templ: device float[gshape2*gshape3].
+ */
+int cytvdn_synth_counts(const int64_t *gshape, int64_t offset0, int64_t lshape0, int dtype,
+                        const float *scan_mod_dev, const float *templ_dev, double counts,
+                        uint64_t seed, void *out_dev, void *stream);
+
+/* Small helpers so that a ctypes host needs no other CUDA binding. */
+int cytvdn_malloc(void **ptr, int64_t bytes);
+int cytvdn_free(void *ptr);
+int cytvdn_host_alloc(void **ptr, int64_t bytes);      /* pinned host memory */
+int cytvdn_host_free(void *ptr);
+int cytvdn_memcpy(void *dst, const void *src, int64_t bytes, void *stream);   /* any direction */
+int cytvdn_memset(void *dst, int value, int64_t bytes, void *stream);
+int cytvdn_stream_synchronize(void *stream);
+int cytvdn_set_device(int device);
+int cytvdn_get_device(int *device);
+int cytvdn_mem_info(int64_t *free_bytes, int64_t *total_bytes);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t cytvdn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYTVDN_B200_H */

@@ -1,0 +1,424 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the cytvdn_b200 shim) against
+ (1) the golden vectors produced by the unmodified reference,
+ (2) the CPU oracle (oracle/tv_oracle.c, pinned to the reference by tests/test_oracle_pin.py) on
+     seeded count-like inputs -- odd shapes, several strips, periodic boundary, half-isotropic,
+ (3) size-independent properties at the full BASELINE config-3 size.
+
+Bar: per-voxel arrays (recon, accumulators, FISTA auxiliaries) BIT-EXACT for the anisotropic
+path in fp32 and fp64 (the kernels round every operation like the reference's x86-64 build);
+half-isotropic within 1e-4 x data range (fp32) / 1e-10 (fp64) -- north_star's tolerance -- because
+`hypot` is not guaranteed bit-identical between glibc and CUDA; bnorm / delta within 1e-4
+relative of the float64-accumulated truth.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INDEX = json.load(open(os.path.join(GOLDEN, "index.json")))
+DENOISE = sorted(k for k, v in INDEX.items() if v["kind"] == "denoise")
+
+RTOL_SCALAR = 1e-4          # north_star: bnorm/delta within 1e-4 relative
+
+
+@pytest.fixture(scope="module")
+def tv():
+    import cytvdn_b200 as tv
+    if tv.device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests must run on a GPU box")
+    return tv
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import tv_oracle
+    tv_oracle.set_threads(tv_oracle.max_threads())
+    return tv_oracle
+
+
+@pytest.fixture(scope="module")
+def steps():
+    return np.load(os.path.join(GOLDEN, "steps.npz"))
+
+
+def counts(rng, shape, dtype, lo=20.0, hi=400.0):
+    mean = rng.uniform(lo, hi, size=shape)
+    for ax in range(len(shape)):
+        mean = 0.5 * (mean + np.roll(mean, 1, axis=ax))
+    return rng.poisson(mean).astype(dtype)
+
+
+def _kwargs(z, meta):
+    kw = dict(meta["kwargs"])
+    if kw.get("reference_data"):
+        kw["reference_data"] = z["reference_data"]
+    if "lam" in kw:
+        kw["lam"] = z["lam"]
+    return kw
+
+
+def _tol(dt, data):
+    rng_ = float(data.max() - data.min()) if data.size else 1.0
+    return (1e-4 * max(rng_, 1.0)) if np.dtype(dt) == np.float32 else 1e-10
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) golden vectors of the reference
+# ------------------------------------------------------------------------------------------------
+def test_step_kernels_match_reference_vectors(tv, steps):
+    n = 0
+    for key in steps.files:
+        if key.startswith("acc_") and key.endswith("_in"):
+            base = key[:-3]
+            a, b, d = steps[key]
+            nd = a.ndim
+            ax, bc = int(base.split("_ax")[1][0]), int(base.split("_bc")[1][0])
+            n1, n2, clip, tk = steps[base + "_norms"]
+            f_plain = tv.accumulator_update_4D if nd == 4 else tv.accumulator_update_3D
+            f_fista = tv.accumulator_update_4D_FISTA if nd == 4 else tv.accumulator_update_3D_FISTA
+            b1 = b.copy()
+            r1 = f_plain(a, b1, ax, clip, bc)
+            assert np.array_equal(b1, steps[base + "_plain"]), base
+            assert r1 == pytest.approx(n1, rel=1e-5), base
+            b2, d2 = b.copy(), d.copy()
+            r2 = f_fista(a, b2, d2, tk, ax, clip, bc)
+            assert np.array_equal(np.stack([b2, d2]), steps[base + "_fista"]), base
+            assert r2 == pytest.approx(n2, rel=1e-5), base
+            n += 1
+        elif key.startswith("dcu_") and key.endswith("_in"):
+            base = key[:-3]
+            arrs = steps[key]
+            f, u, bs = arrs[0], arrs[1].copy(), [x.copy() for x in arrs[2:]]
+            bc = int(base.split("_bc")[1][0])
+            fn = tv.datacube_update_4D if f.ndim == 4 else tv.datacube_update_3D
+            r = fn(f, u, *bs, steps[base + "_w"], bc)
+            assert np.array_equal(u, steps[base + "_out"]), base
+            assert r == pytest.approx(steps[base + "_ratio"][0], rel=1e-5), base
+            n += 1
+        elif key.startswith("iso_") and key.endswith("_in"):
+            base = key[:-3]
+            a, b1, b2, d1, d2 = steps[key]
+            p, q = int(base.split("_p")[1][0]), int(base.split("q")[-1])
+            n1, n2, clip, tk = steps[base + "_norms"]
+            tol = 1e-5 if a.dtype == np.float32 else 1e-12
+            x1, x2 = b1.copy(), b2.copy()
+            r1 = tv.iso_accumulator_update_4D(a, x1, x2, p, q, clip)
+            np.testing.assert_allclose(np.stack([x1, x2]), steps[base + "_plain"], rtol=tol, atol=tol)
+            assert r1 == pytest.approx(n1, rel=1e-5), base
+            y1, y2, e1, e2 = b1.copy(), b2.copy(), d1.copy(), d2.copy()
+            r2 = tv.iso_accumulator_update_4D_FISTA(a, y1, y2, e1, e2, tk, p, q, clip)
+            np.testing.assert_allclose(np.stack([y1, y2, e1, e2]), steps[base + "_fista"], rtol=tol, atol=tol)
+            assert r2 == pytest.approx(n2, rel=1e-5), base
+            n += 1
+        elif key.startswith("sse_") and not key.endswith("_in"):
+            a, b = steps[key + "_in"]
+            fn = tv.sum_square_error_4D if a.ndim == 4 else tv.sum_square_error_3D
+            assert fn(a, b) == pytest.approx(steps[key][0], rel=1e-5), key
+            n += 1
+    assert n > 100
+
+
+@pytest.mark.parametrize("name", DENOISE)
+def test_denoise_matches_reference_driver(tv, name):
+    """tv.denoise3D/4D of this package vs the same call on the unmodified reference."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = INDEX[name]
+    fn = tv.denoise4D if meta["ndim"] == 4 else tv.denoise3D
+    data = z["data"].copy()
+    out = fn(data, z["mu"], quiet=True, **_kwargs(z, meta))
+    assert np.array_equal(data, z["data"]), "input was modified"
+    recon = out[0]
+    assert isinstance(recon, np.ndarray) and recon.dtype == z["recon"].dtype and recon.shape == z["recon"].shape
+    assert out[1].dtype == z["b_norm"].dtype and out[1].shape == z["b_norm"].shape
+    iso = meta["kwargs"].get("isotropic_R") or meta["kwargs"].get("isotropic_Q")
+    if iso:
+        assert float(np.abs(recon - z["recon"]).max()) <= _tol(recon.dtype, data)
+    else:
+        assert np.array_equal(recon, z["recon"]), f"max diff {np.abs(recon - z['recon']).max()}"
+    # same number of executed iterations (trailing zeros after an early stop) and same scalars
+    assert np.count_nonzero(out[2]) == np.count_nonzero(z["delta_recon"])
+    rt = 3e-5 if recon.dtype == np.float32 else 1e-11
+    np.testing.assert_allclose(out[1], z["b_norm"], rtol=rt)
+    np.testing.assert_allclose(out[2], z["delta_recon"], rtol=20 * rt, atol=1e-12)
+    if "MSE" in z.files:
+        assert len(out) == 4
+        np.testing.assert_allclose(out[3], z["MSE"], rtol=rt)
+    else:
+        assert len(out) == 3
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) CPU oracle on seeded inputs
+# ------------------------------------------------------------------------------------------------
+CASES_4D = [
+    # shape, dtype, kwargs, l2 budget MB (small budgets force several strips + a partial one)
+    ((9, 13, 16, 32), "float32", dict(iterations=25, FISTA=True), None),
+    ((9, 13, 16, 32), "float32", dict(iterations=25, FISTA=True), 0.05),
+    ((7, 10, 9, 11), "float32", dict(iterations=20, FISTA=True), 0.01),      # odd extents: scalar path
+    ((6, 7, 5, 6), "float64", dict(iterations=30, FISTA=True), 0.002),
+    ((12, 9, 8, 16), "float64", dict(iterations=20, FISTA=False), None),
+    ((8, 8, 16, 16), "float32", dict(iterations=[10, 10]), 0.03),
+    ((8, 9, 12, 20), "float32", dict(iterations=15, FISTA=True, BC_mode=0), 0.03),
+    ((5, 6, 7, 8), "float64", dict(iterations=15, FISTA=False, BC_mode=0), None),
+    ((1, 7, 8, 8), "float32", dict(iterations=10, FISTA=True), None),
+    ((7, 1, 8, 8), "float32", dict(iterations=10, FISTA=True), None),
+    ((4, 5, 1, 8), "float32", dict(iterations=10, FISTA=True), None),
+    ((4, 5, 8, 1), "float32", dict(iterations=10, FISTA=True), None),
+    ((2, 2, 2, 2), "float32", dict(iterations=10, FISTA=True), None),
+    ((16, 16, 32, 32), "float32", dict(iterations=100, FISTA=True), 0.5),
+]
+
+
+@pytest.mark.parametrize("shape,dt,kw,budget", CASES_4D)
+def test_denoise4d_vs_oracle(tv, O, shape, dt, kw, budget, monkeypatch):
+    if budget is not None:
+        monkeypatch.setenv("CYTVDN_L2_BUDGET_MB", str(budget))
+    rng = np.random.default_rng(abs(hash((shape, dt))) % 2**32)
+    data = counts(rng, shape, dt)
+    mu = np.array([1, 1, .5, .5], dtype=dt)
+    ref = O.denoise4D(data, mu, quiet=True, kernels=O.PortKernels("D"), scalars="D", **kw)
+    out = tv.denoise4D(data, mu, quiet=True, **kw)
+    assert np.array_equal(out[0], ref[0]), f"max diff {np.abs(out[0] - ref[0]).max()}"
+    np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
+    np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR, atol=1e-30)
+
+
+CASES_3D = [
+    ((9, 11, 64), "float32", dict(iterations=30, FISTA=False), None),
+    ((9, 11, 64), "float32", dict(iterations=30, FISTA=True), 0.004),
+    ((7, 5, 37), "float32", dict(iterations=20, FISTA=True), 0.001),
+    ((6, 9, 50), "float64", dict(iterations=25, FISTA=True, BC_mode=0), 0.002),
+    ((5, 1, 16), "float32", dict(iterations=8, FISTA=True), None),
+    ((1, 1, 1), "float64", dict(iterations=3, FISTA=False), None),
+    ((12, 12, 256), "float32", dict(iterations=100, FISTA=True), 0.05),
+]
+
+
+@pytest.mark.parametrize("shape,dt,kw,budget", CASES_3D)
+def test_denoise3d_vs_oracle(tv, O, shape, dt, kw, budget, monkeypatch):
+    if budget is not None:
+        monkeypatch.setenv("CYTVDN_L2_BUDGET_MB", str(budget))
+    rng = np.random.default_rng(abs(hash((shape, dt))) % 2**32)
+    data = counts(rng, shape, dt)
+    mu = np.array([1, 1, .5], dtype=dt)
+    it = kw.pop("iterations")
+    ref = O.denoise3D(data, mu, it, quiet=True, kernels=O.PortKernels("D"), scalars="D", **kw)
+    out = tv.denoise3D(data, mu, it, quiet=True, **kw)
+    kw["iterations"] = it
+    assert np.array_equal(out[0], ref[0]), f"max diff {np.abs(out[0] - ref[0]).max()}"
+    np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR, atol=1e-30)
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+@pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("fista", [True, False])
+def test_half_isotropic_vs_oracle(tv, O, dt, flags, fista):
+    rng = np.random.default_rng(11)
+    data = counts(rng, (8, 9, 12, 16), dt)
+    mu = np.array([1, 1, .5, .5], dtype=dt)
+    kw = dict(iterations=25, FISTA=fista, isotropic_R=flags[0], isotropic_Q=flags[1])
+    ref = O.denoise4D(data, mu, quiet=True, kernels=O.PortKernels("D"), scalars="D", **kw)
+    out = tv.denoise4D(data, mu, quiet=True, **kw)
+    assert float(np.abs(out[0] - ref[0]).max()) <= _tol(dt, data)
+    np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
+    np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR)
+
+
+def test_early_stop_and_hybrid_semantics(tv, O):
+    rng = np.random.default_rng(3)
+    data = counts(rng, (8, 8, 8, 16), "float32")
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = O.denoise4D(data, mu, 40, True, 0.02, quiet=True, kernels=O.PortKernels("D"), scalars="D")
+    out = tv.denoise4D(data, mu, 40, True, 0.02, quiet=True)
+    n = np.count_nonzero(ref[2])
+    assert 0 < n < 40 and np.count_nonzero(out[2]) == n and np.all(out[2][n:] == 0) and np.all(out[1][n:] == 0)
+    assert np.array_equal(out[0], ref[0])
+    # hybrid list with early stop inside the FISTA phase: the unaccelerated phase still runs
+    ref = O.denoise4D(data, mu, [30, 5], True, 0.02, quiet=True, kernels=O.PortKernels("D"), scalars="D")
+    out = tv.denoise4D(data, mu, [30, 5], True, 0.02, quiet=True)
+    assert np.array_equal(out[0], ref[0])
+    assert np.array_equal(out[2] != 0, ref[2] != 0)
+
+
+def test_api_errors_and_edge_cases(tv):
+    f32 = np.float32
+    data = np.ones((2, 3, 4, 4), f32)
+    mu = np.array([1, 1, .5, .5], f32)
+    with pytest.raises(AssertionError, match="datacube must be floating point datatype."):
+        tv.denoise4D(data.astype(np.int32), mu, 2, quiet=True)
+    with pytest.raises(AssertionError, match="Mu must have same dtype as datacube."):
+        tv.denoise4D(data, mu.astype(np.float64), 2, quiet=True, lam=mu / 32)
+    with pytest.raises(AssertionError, match="Lambda must have same dtype as datacube."):
+        tv.denoise4D(data, mu, 2, quiet=True, lam=(mu / 32).astype(np.float64))
+    with pytest.raises(AssertionError, match="C-contiguous"):
+        tv.denoise4D(np.asfortranarray(data), mu, 2, quiet=True)
+    with pytest.raises(AssertionError, match="Parameters must satisfy"):
+        tv.denoise3D(np.ones((2, 3, 4), f32), np.ones(3, f32), 2, quiet=True, lam=np.ones(3, f32))
+    with pytest.raises(NotImplementedError):
+        tv.denoise4D(data, mu, 2, BC_mode=1, quiet=True)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        tv.accumulator_update_4D(data, data.astype(np.float64), 0, 1.0)
+    with pytest.raises(TypeError, match="No matching signature found"):
+        tv.accumulator_update_4D(data[0], data[0].copy(), 0, 1.0)
+    # constant input: recon == input, bnorm == 0, delta == 0
+    r, bn, dl = tv.denoise4D(data, mu, 3, quiet=True)
+    assert np.array_equal(r, data) and np.all(bn == 0) and np.all(dl == 0)
+    # all-zero input: C division 0/0 -> nan, no exception (utils.pyx:125)
+    r, bn, dl = tv.denoise4D(np.zeros_like(data), mu, 2, quiet=True)
+    assert np.all(r == 0) and np.all(bn == 0) and np.all(np.isnan(dl))
+    # zero iterations: a copy of the input
+    r, bn, dl = tv.denoise4D(data, mu, 0, quiet=True)
+    assert np.array_equal(r, data) and bn.shape == (0,)
+    # NaN propagates through the comparison-based clip
+    a = data.copy(); a[1, 1, 1, 1] = np.nan
+    b = np.zeros_like(a)
+    tv.accumulator_update_4D(a, b, 3, 5.0)
+    assert np.isnan(b[1, 1, 1, 1]) and np.isnan(b[1, 1, 1, 2]) and np.isfinite(b[1, 1, 1, 0])
+
+
+def test_torch_tensors_in_place(tv, O):
+    import torch
+    rng = np.random.default_rng(8)
+    data = counts(rng, (6, 7, 8, 16), "float32")
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = O.denoise4D(data, mu, 12, True, quiet=True, kernels=O.PortKernels("D"), scalars="D")
+    t = torch.from_numpy(data).cuda()
+    out = tv.denoise4D(t, mu, 12, True, quiet=True)
+    assert out[0].is_cuda and torch.equal(t.cpu(), torch.from_numpy(data))
+    assert np.array_equal(out[0].cpu().numpy(), ref[0])
+    # step function on device tensors: in place, no copies
+    a = torch.from_numpy(data).cuda()
+    b = torch.zeros_like(a)
+    K = O.PortKernels("D")
+    bh = np.zeros_like(data)
+    want = K.accumulator_update(data, bh, None, 0.0, 1, 32.0, 2)
+    got = tv.accumulator_update_4D(a, b, 1, 32.0)
+    assert np.array_equal(b.cpu().numpy(), bh) and got == pytest.approx(want, rel=1e-9)
+
+
+def test_step_opts_box_owned_range_and_zero_wrap(tv, O):
+    """The sharding extras of the C ABI against a NumPy emulation with the oracle."""
+    import ctypes as C
+    import torch
+    from cytvdn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    shape = (7, 6, 8, 8)
+    a = counts(rng, shape, "float32")
+    b0 = rng.normal(0, 20, shape).astype(np.float32)
+    K = O.PortKernels("D")
+    # oracle on the whole array; the launch covers planes 2..5 / columns 1..5, reduction over 3..4 / 2..4
+    full = b0.copy()
+    K.accumulator_update(a, full, None, 0.0, 0, 32.0, 2)
+    want_b = b0.copy()
+    want_b[2:5, 1:5] = full[2:5, 1:5]
+    want_norm = float(np.abs(full[3:4, 2:4], dtype=np.float64).sum())
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b0).cuda()
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+    o = _lib.StepOpts()
+    o.box_lo[0], o.box_hi[0], o.box_lo[1], o.box_hi[1] = 2, 5, 1, 5
+    o.own_lo[0], o.own_hi[0], o.own_lo[1], o.own_hi[1] = 3, 4, 2, 4
+    sh = (C.c_int64 * 4)(*shape)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.cytvdn_accumulator_update(4, sh, 0, ta.data_ptr(), tb.data_ptr(), None, 0.0, 0, 32.0, 2,
+                                             sums.data_ptr(), C.byref(o), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(tb.cpu().numpy(), want_b)
+    assert float(sums[0]) == pytest.approx(want_norm, rel=1e-6)   # fp32 partial sums of 4 before float64
+    # zero-wrap: the forward neighbour of the last plane on axis 0 is 0 instead of plane 0
+    bs = [rng.normal(0, 30, shape).astype(np.float32) for _ in range(4)]
+    w = np.array([1 / 32, 1 / 32, 1 / 64, 1 / 64], np.float32)
+    u = a.copy()
+    ext = [np.concatenate([x, np.zeros_like(x[:1])], axis=0) if k == 0 else
+           np.concatenate([x, x[:1]], axis=0) for k, x in enumerate(bs)]   # plane 7 := 0 for b0
+    ue = np.concatenate([u, u[:1]], axis=0)
+    fe = np.concatenate([a, a[:1]], axis=0)
+    K.datacube_update(fe, ue, ext, w)
+    want_u = ue[:7]
+    tu = torch.from_numpy(u).cuda()
+    tbs = [torch.from_numpy(x).cuda() for x in bs]
+    bp = (C.c_void_p * 4)(*[x.data_ptr() for x in tbs])
+    wd = (C.c_double * 4)(*[float(x) for x in w])
+    o2 = _lib.StepOpts()
+    o2.zero_wrap_mask = 1
+    _lib.check(lib.cytvdn_datacube_update(4, sh, 0, ta.data_ptr(), tu.data_ptr(), tu.data_ptr(), bp, wd, 2,
+                                          sums.data_ptr(), C.byref(o2), st))
+    torch.cuda.synchronize()
+    got = tu.cpu().numpy()
+    # every plane except the last sees its true forward neighbour; the last sees 0 on axis 0.
+    # (axis 1..3 wrap inside a plane, unaffected by the extra plane of the emulation)
+    assert np.array_equal(got[:6], want_u[:6])
+    assert np.array_equal(got[6], want_u[6])
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) properties at BASELINE config-3 size (256 x 256 x 128 x 128 fp32, 4-D FISTA)
+# ------------------------------------------------------------------------------------------------
+def _synth(shape, seed=2, counts_=500.0):
+    from cytvdn_b200 import synth
+    return synth.stem4d_device(shape, seed=seed, counts=counts_)
+
+
+def test_fullsize_reductions_and_determinism(tv):
+    """One FISTA iteration on the full config-3 array: the fused reductions equal float64 sums of
+    the arrays (torch), and a second run is bit-identical."""
+    import ctypes as C
+    import torch
+    from cytvdn_b200 import _lib
+    lib = _lib.load()
+    shape = (256, 256, 128, 128)
+    x = _synth(shape)
+    assert float(x.max()) > 300 and float(x.min()) >= 0
+    sh = (C.c_int64 * 4)(*shape)
+    st = torch.cuda.current_stream().cuda_stream
+    clip = (C.c_double * 4)(32.0, 32.0, 64.0, 64.0)
+    w = (C.c_double * 4)(*[1 / 32.0] * 4)
+    results = []
+    for rep in range(2):
+        b = [torch.zeros_like(x) for _ in range(4)]
+        d = [torch.zeros_like(x) for _ in range(4)]
+        u = x.clone()
+        sums = torch.zeros(8, dtype=torch.float64, device="cuda")
+        bp = (C.c_void_p * 4)(*[t.data_ptr() for t in b])
+        dp = (C.c_void_p * 4)(*[t.data_ptr() for t in d])
+        for it, tk in enumerate((0.0, 0.28)):
+            _lib.check(lib.cytvdn_accumulator_update_all(4, sh, 0, u.data_ptr(), bp, dp, tk, clip, 0, 0, 2,
+                                                         sums.data_ptr(), None, st))
+            old = u.clone()
+            _lib.check(lib.cytvdn_datacube_update(4, sh, 0, x.data_ptr(), u.data_ptr(), u.data_ptr(), bp, w, 2,
+                                                  sums.data_ptr() + 8, None, st))
+        torch.cuda.synchronize()
+        bn = sum(float(t.abs().sum(dtype=torch.float64)) for t in b)
+        dn = float((u - old).abs().sum(dtype=torch.float64))
+        on = float(old.abs().sum(dtype=torch.float64))
+        s = sums.cpu().numpy()
+        assert s[0] == pytest.approx(bn, rel=1e-9)
+        assert s[1] == pytest.approx(dn, rel=1e-9) and s[2] == pytest.approx(on, rel=1e-9)
+        # Jia-Zhao invariant: plane 0 of every accumulator stays 0 on its own axis
+        assert float(b[0][0].abs().max()) == 0 and float(b[1][:, 0].abs().max()) == 0
+        assert float(b[2][:, :, 0].abs().max()) == 0 and float(b[3][..., 0].abs().max()) == 0
+        assert float(b[2].abs().max()) == 64.0 and float(b[0].abs().max()) == 32.0     # clip is active
+        results.append((s.copy(), float(u.sum(dtype=torch.float64)), int(u.view(torch.int32).sum(dtype=torch.int64))))
+        del b, d, u, old
+    assert np.array_equal(results[0][0], results[1][0]) and results[0][1:] == results[1][1:]
+
+
+def test_fullsize_periodic_shift_equivariance(tv):
+    """BC_mode=0 is translation invariant: denoise(roll(x)) == roll(denoise(x)) bit for bit, which
+    exercises every strip / tile boundary at full size (128 x 256 x 128 x 128 here: 4 + 4 arrays)."""
+    import torch
+    shape = (128, 256, 128, 128)
+    x = _synth(shape, seed=5)
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    r1 = tv.denoise4D(x, mu, 3, False, BC_mode=0, quiet=True)[0]
+    xs = torch.roll(x, shifts=(5, 3, 7, 9), dims=(0, 1, 2, 3)).contiguous()
+    del x
+    r2 = tv.denoise4D(xs, mu, 3, False, BC_mode=0, quiet=True)[0]
+    del xs
+    assert torch.equal(torch.roll(r1, shifts=(5, 3, 7, 9), dims=(0, 1, 2, 3)), r2)
