@@ -1,0 +1,126 @@
+"""bench.py's N > 1 arm: BASELINE config 5 (4-D anisotropic FISTA, fp32, scan-axis shards with a one-plane
+halo exchange), weak scaling with 128x1024x128x128 owned per GPU.  Launched by torchrun, one rank per GPU."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+
+def run_sharded(args):
+    import torch
+    import torch.distributed as dist
+    import cytvdn_b200 as tv
+    from cytvdn_b200 import sharded, synth
+    from bench import (BYTES_A, BYTES_B, METRIC, MU, SHARD_PER_GPU, UNIT, ClockSampler, measured_peak,
+                       workload_config)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        per = tuple(args.shape) if args.shape else SHARD_PER_GPU
+        gshape = (per[0] * world,) + tuple(per[1:])
+        plan = sharded.ShardPlan(gshape, world, rank)
+        n0 = plan.local_shape[0]
+        x = synth.stem4d_device(gshape, offset0=plan.read[0][0], lshape0=n0, seed=2, counts=500.0, device=dev)
+        mu = np.array(MU, dtype=np.float32)
+        n_total = args.warmup + args.steps
+        sh = sharded.CudaShard(plan, x, mu, None, fista=True, n_iter=n_total)
+        comm_stream = torch.cuda.Stream(device=dev)
+        tk = 1.0
+        it = 0
+
+        def step():
+            nonlocal tk, it
+            tkr, tk = sharded.fista_ratio(tk)
+            sharded._run_iteration_overlapped(sh, it, tkr, True, None, comm_stream)
+            it += 1
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local) if rank == 0 else None
+        if clocks:
+            clocks.start()
+            time.sleep(0.3)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = sh.launches
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        total_ms = float(ms[0])
+        launches = torch.tensor([sh.launches - l0], dtype=torch.int64, device=dev)
+        dist.all_reduce(launches)
+        clk = clocks.stop() if clocks else None
+        gvox = int(np.prod(gshape))
+        value = gvox * args.steps / (total_ms * 1e-3) / 1e9
+        glob = sh.local_sums().clone()
+        dist.all_reduce(glob)
+        last = glob[it - 1].cpu().numpy()
+        peak, peak_src = measured_peak()
+        local_vox = int(np.prod(plan.local_shape))
+        ms_per_step = total_ms / args.steps
+        ach = (BYTES_A + BYTES_B) * local_vox / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "per-GPU iteration: half-step A + half-step B sweeps incl. halo planes "
+                                              "(96 B/voxel over the stored block)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src}
+        # ---- end to end through the public sharded API with pinned host buffers ----------------------
+        e2e = None
+        del sh
+        torch.cuda.empty_cache()
+        if not args.no_e2e:
+            try:
+                iters = args.e2e_iters
+                host_in = tv.pinned_empty(plan.local_shape, np.float32)
+                host_out = tv.pinned_empty(plan.local_shape, np.float32)
+                torch.from_numpy(host_in).copy_(x)
+                del x
+                torch.cuda.empty_cache()
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+                xd = torch.empty(plan.local_shape, dtype=torch.float32, device=dev)
+                xd.copy_(torch.from_numpy(host_in), non_blocking=True)
+                recon, bn, dl = sharded.denoise4D_sharded(xd, mu, iters, True, plan=plan)
+                torch.from_numpy(host_out).copy_(recon, non_blocking=True)
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                nbytes = int(np.prod(plan.local_shape)) * 4
+                e2e = {"value": gvox * iters / float(dt[0]) / 1e9, "unit": UNIT,
+                       "h2d_bytes_per_step": nbytes * world / iters, "d2h_bytes_per_step": nbytes * world / iters,
+                       "call": f"sharded.denoise4D_sharded(shard from pinned host, iterations={iters}, FISTA=True) on every rank",
+                       "wall_s": float(dt[0]), "delta_last": float(dl[-1])}
+            except Exception as e:          # e.g. not enough pinned host memory on this box
+                e2e = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
+        if rank == 0:
+            line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": workload_config(world) if not args.shape else
+                    {"workload": f"4-D FISTA fp32 sharded, {'x'.join(map(str, per))} per GPU (non-default)"},
+                    "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches[0]),
+                    "clocks": clk,
+                    "check": {"bnorm_last": float(last[0]), "delta_last": float(last[1] / last[2]) if last[2] else None}}
+            print(json.dumps(line), flush=True)
+    finally:
+        dist.destroy_process_group()
+    return 0

@@ -390,3 +390,70 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
     if return_state:
         return sh.recon, b_norm, delta, sh
     return sh.recon, b_norm, delta
+
+
+# ------------------------------------------------------------------------------------------------
+# all ranks of a plan on ONE device, in lockstep (no process group): used to validate the sharded
+# schedule -- box order, owned-range reductions, zero-wrap, plane indices -- with the real kernels
+# when fewer GPUs than ranks are available.
+# ------------------------------------------------------------------------------------------------
+def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True, split_boxes=True, lam=None):
+    """``gdata``: the GLOBAL array as a CUDA tensor.  Returns (assembled recon, b_norm, delta)."""
+    import torch
+    if type(iterations) in (list, tuple):
+        nF, nU = int(iterations[0]), int(iterations[1])
+    else:
+        nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
+    n = nF + nU
+    plans = [ShardPlan(gdata.shape, world, r, grid) for r in range(world)]
+    shards = [CudaShard(p, gdata[p.read_global].contiguous(), mu, lam, fista=nF > 0, n_iter=n) for p in plans]
+    one_d = plans[0].grid[1] == 1
+
+    def exchange(phase):
+        sent = {}
+        for s in shards:
+            for op in (s.plan.after_a() if phase == "a" else s.plan.after_b()):
+                if op.kind == "send":
+                    sent[(s.plan.rank, op.peer, op.array, op.axis)] = plane(s.arrays[op.array], op.axis, op.index).clone()
+        for s in shards:
+            for op in (s.plan.after_a() if phase == "a" else s.plan.after_b()):
+                if op.kind == "recv":
+                    plane(s.arrays[op.array], op.axis, op.index).copy_(sent.pop((op.peer, s.plan.rank, op.array, op.axis)))
+        assert not sent
+
+    tk = 1.0
+    for phase_f, cnt in ((0, nF), (1, nU)):
+        for j in range(cnt):
+            it = j if phase_f == 0 else nF + j
+            tkr = 0.0
+            if phase_f == 0:
+                tkr, tk = fista_ratio(tk)
+            for phase in ("a", "b"):
+                if split_boxes and one_d:
+                    slots = {}
+                    for s in shards:
+                        first, _ = s.plan.a_boxes() if phase == "a" else s.plan.b_boxes()
+                        slot = 0 if phase == "a" else 4
+                        for box in first:
+                            (s.half_step_a(it, slot, tkr, phase_f == 0, box) if phase == "a" else s.half_step_b(it, slot, box))
+                            slot += 1 if phase == "a" else 2
+                        slots[s.plan.rank] = slot
+                    exchange(phase)        # in the real schedule this runs under the "rest" sweep
+                    for s in shards:
+                        _, rest = s.plan.a_boxes() if phase == "a" else s.plan.b_boxes()
+                        slot = slots[s.plan.rank]
+                        for box in rest:
+                            (s.half_step_a(it, slot, tkr, phase_f == 0, box) if phase == "a" else s.half_step_b(it, slot, box))
+                            slot += 1 if phase == "a" else 2
+                else:
+                    for s in shards:
+                        (s.half_step_a(it, 0, tkr, phase_f == 0) if phase == "a" else s.half_step_b(it, 4))
+                    exchange(phase)
+    out = torch.empty_like(gdata)
+    tot = torch.zeros((max(n, 1), 3), dtype=torch.float64, device=gdata.device)
+    for s in shards:
+        out[s.plan.owned_global] = s.recon[s.plan.owned_local]
+        tot += s.local_sums()
+    g = tot.cpu().numpy()
+    with np.errstate(all="ignore"):
+        return out, g[:n, 0].copy(), (g[:n, 1] / g[:n, 2]).copy()

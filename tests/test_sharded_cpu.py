@@ -1,0 +1,155 @@
+"""Host-side logic of the scan-axis sharding (cytvdn_b200/sharded.py) on CPU.
+
+The partition, the halo plane indices, the zero-wrap rule and ``halo_exchange`` are the product
+code; the arithmetic is done by the oracle's kernels (tests/sharded_cpu_driver.py).  The oracle for
+the sharded result is the single-process ``denoise4D`` on the unsharded array (SURVEY.md section 8c:
+`mpi.py`'s as-written exchange does not reproduce it and the reference has no sharded FISTA)."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+
+from cytvdn_b200.sharded import ShardPlan, mpi_grid
+from oracle import tv_oracle as O
+from tests import sharded_cpu_driver as drv
+
+
+def counts(rng, shape):
+    return rng.poisson(rng.uniform(20, 400, shape)).astype(np.float32)
+
+
+def test_mpi_grid_heuristic_matches_reference():
+    # square scan -> 2 ranks (1,2), 4 -> (2,2), 8 -> (2,4)  (mpi.py:131-150)
+    assert mpi_grid((256, 256), 2) == (1, 2)
+    assert mpi_grid((256, 256), 4) == (2, 2)
+    assert mpi_grid((256, 256), 8) == (2, 4)
+    assert mpi_grid((1024, 64), 4) == (4, 1)
+    assert mpi_grid((10, 10), 1) == (1, 1)
+
+
+@pytest.mark.parametrize("gshape,world,grid", [
+    ((12, 10, 3, 4), 1, None), ((12, 10, 3, 4), 2, None), ((13, 10, 3, 4), 4, None), ((12, 10, 3, 4), 4, (2, 2)),
+    ((13, 11, 3, 4), 6, (3, 2)), ((16, 16, 2, 2), 8, "mpi"), ((9, 20, 2, 2), 4, (1, 4)),
+])
+def test_plan_tiles_the_global_array(gshape, world, grid):
+    cover = np.zeros(gshape[:2], dtype=int)
+    for r in range(world):
+        p = ShardPlan(gshape, world, r, grid)
+        cover[p.owned_global] += 1
+        # stored block = owned block + one plane towards each existing neighbour (mpi.py:173-196)
+        for k in range(2):
+            assert p.read[k][0] == p.valid[k][0] - (1 if p.has_lo[k] else 0)
+            assert p.read[k][1] == p.valid[k][1] + (1 if p.has_hi[k] else 0)
+            assert p.own_hi[k] - p.own_lo[k] == p.valid[k][1] - p.valid[k][0]
+        # every send has its matching receive on the peer, with the corrected plane indices
+        for phase in ("after_a", "after_b"):
+            for op in getattr(p, phase)():
+                q = ShardPlan(gshape, world, op.peer, grid)
+                mirror = [o for o in getattr(q, phase)() if o.peer == r and o.array == op.array and o.axis == op.axis
+                          and o.kind != op.kind]
+                assert len(mirror) == 1
+                # the global index of the plane sent equals the global index of the plane received
+                g_here = p.read[op.axis][0] + op.index
+                g_there = q.read[op.axis][0] + mirror[0].index
+                assert g_here == g_there
+                if op.kind == "send":          # only owned planes are ever sent
+                    assert p.valid[op.axis][0] <= g_here < p.valid[op.axis][1]
+    assert np.all(cover == 1)
+
+
+def test_plan_rejects_empty_tiles():
+    with pytest.raises(ValueError, match="empty"):
+        ShardPlan((5, 8, 2, 2), 4, 3, None)        # ceil(5/4)=2 planes per tile -> tile 3 empty
+
+
+def test_boxes_partition_axis0():
+    for world, rank in ((1, 0), (2, 0), (2, 1), (4, 2)):
+        p = ShardPlan((16, 6, 2, 2), world, rank)
+        n = p.local_shape[0]
+        fa, ra = p.a_boxes()
+        seen = sorted(i for lo, hi in fa + ra for i in range(lo, hi))
+        assert seen == list(range(n))
+        fb, rb = p.b_boxes()
+        seen = sorted(i for lo, hi in fb + rb for i in range(lo, hi))
+        assert seen == list(range(n - (1 if p.has_hi[0] else 0)))       # received overlap plane skipped
+        if p.has_lo[0]:
+            assert (1, 2) in fb and (0, 1) in fa
+        if p.has_hi[0]:
+            assert (n - 2, n - 1) in fa
+
+
+@pytest.mark.parametrize("world,grid", [(1, None), (2, None), (2, (1, 2)), (3, None), (4, None), (4, (2, 2)),
+                                        (6, (3, 2)), (6, (2, 3)), (8, "mpi")])
+@pytest.mark.parametrize("fista", [True, False])
+def test_in_process_emulation_equals_single_process(world, grid, fista):
+    """All ranks emulated sequentially (uneven splits included): assembled recon == unsharded recon."""
+    O.set_threads(O.max_threads())
+    rng = np.random.default_rng(17 + world)
+    gshape = (13, 10, 6, 5) if world != 8 else (13, 14, 6, 5)
+    data = counts(rng, gshape)
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    K = O.PortKernels("D")
+    n = 12
+    ref = O.denoise4D(data, mu, n, fista, quiet=True, kernels=K, scalars="D")
+    got, bn, dl = drv.run_in_process(data, mu, world, grid, n if fista else 0, 0 if fista else n, K)
+    assert np.array_equal(got, ref[0]), f"max diff {np.abs(got - ref[0]).max()}"
+    np.testing.assert_allclose(bn, ref[1], rtol=1e-12)
+    np.testing.assert_allclose(dl, ref[2], rtol=1e-10)
+
+
+def test_as_written_mpi_exchange_is_not_equivalent():
+    """Documents why the plane indices differ from mpi.py:325,408 -- sending the overlap planes
+    (acc[-1] / recon[0]) does NOT reproduce the single-process result."""
+    O.set_threads(O.max_threads())
+    rng = np.random.default_rng(3)
+    data = counts(rng, (12, 10, 6, 5))
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    K = O.PortKernels("D")
+    ref = O.denoise4D(data, mu, 8, False, quiet=True, kernels=K, scalars="D")[0]
+    plans = [ShardPlan(data.shape, 2, r) for r in range(2)]
+    sh = [drv.CpuShard(p, np.ascontiguousarray(data[p.read_global]), mu, K, fista=False) for p in plans]
+    for _ in range(8):
+        for s in sh:
+            s.half_step_a(0.0, False)
+        sh[1].b[0][0] = sh[0].b[0][-1]            # as written: mpi.py:325 sends acc0[-1]
+        for s in sh:
+            s.K.datacube_update(s.orig, s.recon, s.b, s.w, 2)
+        sh[0].recon[-1] = sh[1].recon[0]          # as written: mpi.py:408 sends recon[0]
+    got = np.concatenate([sh[0].recon[:-1], sh[1].recon[1:]])
+    assert float(np.abs(got - ref).max()) > 0.1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("grid", [None, (1, 2)])
+def test_gloo_world2_halo_exchange(grid):
+    """Two real ranks over gloo: the product halo_exchange (axis-0 planes contiguous, axis-1 planes
+    staged) and the all-reduced owned sums."""
+    import torch.multiprocessing as mp
+    gshape, seed, nF, nU = (10, 9, 5, 4), 99, 6, 3
+    with tempfile.TemporaryDirectory() as tmp:
+        port = _free_port()
+        mp.spawn(drv.run_distributed_rank, args=(2, port, grid, gshape, seed, nF, nU, tmp), nprocs=2, join=True)
+        rng = np.random.default_rng(seed)
+        data = rng.poisson(rng.uniform(20, 400, gshape)).astype(np.float32)
+        mu = np.array([1, 1, .5, .5], dtype=np.float32)
+        O.set_threads(O.max_threads())
+        ref = O.denoise4D(data, mu, [nF, nU], quiet=True, kernels=O.PortKernels("D"), scalars="D")
+        got = np.empty_like(data)
+        for r in range(2):
+            z = np.load(os.path.join(tmp, f"rank{r}.npz"))
+            lo = z["lo"]
+            blk = z["recon"]
+            got[lo[0]:lo[0] + blk.shape[0], lo[1]:lo[1] + blk.shape[1]] = blk
+            sums = z["sums"]
+        assert np.array_equal(got, ref[0])
+        np.testing.assert_allclose(sums[:, 0], ref[1], rtol=1e-12)
+        np.testing.assert_allclose(sums[:, 1] / sums[:, 2], ref[2], rtol=1e-10)
