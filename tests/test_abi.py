@@ -1,0 +1,113 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/cytvdn_b200.h declares, the ctypes structures match the C layout, the Python mirror keeps the
+reference's signatures, and the product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import inspect
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cytvdn_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cytvdn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cytvdn_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cytvdn_b200.h but not exported"
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes and header disagree"
+    assert lib.cytvdn_version() == 100
+
+
+def test_ctypes_structs_match_c_layout():
+    from cytvdn_b200 import _lib
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "cytvdn_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(cytvdn_step_opts), offsetof(cytvdn_step_opts, own_lo),
+         offsetof(cytvdn_step_opts, zero_wrap_mask), offsetof(cytvdn_step_opts, l2_budget_bytes), (size_t)0);
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(cytvdn_denoise_params), offsetof(cytvdn_denoise_params, shape),
+         offsetof(cytvdn_denoise_params, stopping_relative_change), offsetof(cytvdn_denoise_params, clip),
+         offsetof(cytvdn_denoise_params, device), offsetof(cytvdn_denoise_params, stream));
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "t.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(tmp, "t")
+        gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    a = [int(v) for v in out[0].split()]
+    S = _lib.StepOpts
+    assert a[:4] == [C.sizeof(S), S.own_lo.offset, S.zero_wrap_mask.offset, S.l2_budget_bytes.offset]
+    b = [int(v) for v in out[1].split()]
+    P = _lib.DenoiseParams
+    assert b == [C.sizeof(P), P.shape.offset, P.stopping_relative_change.offset, P.clip.offset, P.device.offset,
+                 P.stream.offset]
+
+
+def test_python_mirror_keeps_reference_signatures():
+    """Names, order and defaults of cyTVDN.py:19-31 and :250-260 (extras are keyword-only)."""
+    import cytvdn_b200 as tv
+    p4 = inspect.signature(tv.denoise4D).parameters
+    pos4 = [(k, v.default) for k, v in p4.items() if v.kind == v.POSITIONAL_OR_KEYWORD]
+    assert pos4 == [("datacube", inspect._empty), ("mu", inspect._empty), ("iterations", 10), ("FISTA", True),
+                    ("stopping_relative_change", None), ("isotropic_R", False), ("isotropic_Q", False),
+                    ("reference_data", None), ("BC_mode", 2), ("lam", None), ("quiet", False)]
+    p3 = inspect.signature(tv.denoise3D).parameters
+    pos3 = [(k, v.default) for k, v in p3.items() if v.kind == v.POSITIONAL_OR_KEYWORD]
+    assert pos3 == [("datacube", inspect._empty), ("mu", inspect._empty), ("iterations", 7500),
+                    ("stopping_relative_change", None), ("BC_mode", 2), ("FISTA", False), ("reference_data", None),
+                    ("lam", None), ("quiet", False)]
+    for name in ("accumulator_update_4D", "accumulator_update_4D_FISTA", "accumulator_update_3D",
+                 "accumulator_update_3D_FISTA", "iso_accumulator_update_4D", "iso_accumulator_update_4D_FISTA",
+                 "datacube_update_4D", "datacube_update_3D", "sum_square_error_4D", "sum_square_error_3D",
+                 "check_memory"):
+        assert callable(getattr(tv, name))
+    assert list(inspect.signature(tv.accumulator_update_4D_FISTA).parameters) == ["a", "b", "d", "tk", "ax", "clip", "BC_mode"]
+    assert list(inspect.signature(tv.iso_accumulator_update_4D_FISTA).parameters) == \
+        ["a", "b1", "b2", "d1", "d2", "tk", "ax1", "ax2", "clip"]
+    assert list(inspect.signature(tv.datacube_update_4D).parameters) == \
+        ["orig", "recon", "b1", "b2", "b3", "b4", "lambda_mu", "BC_mode"]
+
+
+def test_no_cpu_fallback_and_host_side_checks():
+    import cytvdn_b200 as tv
+    data = np.ones((2, 3, 4, 4), np.float32)
+    mu = np.array([1, 1, .5, .5], np.float32)
+    # the reference's assertions fire before anything touches the device
+    with pytest.raises(AssertionError, match="datacube must be floating point datatype."):
+        tv.denoise4D(data.astype(np.int16), mu, 2, quiet=True)
+    with pytest.raises(AssertionError, match="Mu must have same dtype as datacube."):
+        tv.denoise4D(data, mu.astype(np.float64), 2, lam=mu / 32, quiet=True)
+    with pytest.raises(AssertionError, match="Parameters must satisfy"):
+        tv.denoise3D(data[0], np.ones(3, np.float32), 2, lam=np.ones(3, np.float32), quiet=True)
+    if tv.device_count() == 0:
+        with pytest.raises(tv.CytvdnError, match="no CPU fallback"):
+            tv.denoise4D(data, mu, 2, quiet=True)
+        with pytest.raises(tv.CytvdnError, match="no CPU fallback"):
+            tv.accumulator_update_4D(data, np.zeros_like(data), 0, 1.0)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cytvdn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt, f
