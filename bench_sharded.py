@@ -33,7 +33,8 @@ def run_sharded(args):
         x = synth.stem4d_device(gshape, offset0=plan.read[0][0], lshape0=n0, seed=2, counts=500.0, device=dev)
         mu = np.array(MU, dtype=np.float32)
         n_total = args.warmup + args.steps
-        sh = sharded.CudaShard(plan, x, mu, None, fista=True, n_iter=n_total)
+        fused = args.schedule == "fused"
+        sh = sharded.CudaShard(plan, x, mu, None, fista=True, n_iter=n_total, fused=fused)
         comm_stream = torch.cuda.Stream(device=dev)
         tk = 1.0
         it = 0
@@ -41,7 +42,10 @@ def run_sharded(args):
         def step():
             nonlocal tk, it
             tkr, tk = sharded.fista_ratio(tk)
-            sharded._run_iteration_overlapped(sh, it, tkr, True, None, comm_stream)
+            if fused:
+                sharded._run_iteration_fused(sh, it, tkr, True, None, comm_stream)
+            else:
+                sharded._run_iteration_overlapped(sh, it, tkr, True, None, comm_stream)
             it += 1
 
         for _ in range(args.warmup):
@@ -71,17 +75,21 @@ def run_sharded(args):
         clk = clocks.stop() if clocks else None
         gvox = int(np.prod(gshape))
         value = gvox * args.steps / (total_ms * 1e-3) / 1e9
-        glob = sh.local_sums().clone()
+        glob = (sh.fused_local_sums() if fused else sh.local_sums()).clone()
         dist.all_reduce(glob)
         last = glob[it - 1].cpu().numpy()
         peak, peak_src = measured_peak()
         local_vox = int(np.prod(plan.local_shape))
         ms_per_step = total_ms / args.steps
-        ach = (BYTES_A + BYTES_B) * local_vox / (ms_per_step * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "per-GPU iteration: half-step A + half-step B sweeps incl. halo planes "
-                                              "(96 B/voxel over the stored block)",
+        bpv = 76 if fused else (BYTES_A + BYTES_B)
+        ach = bpv * local_vox / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm",
+                    "kernel": ("per-GPU iteration: tv_fused_kernel sweeps incl. halo planes (76 B/voxel over the stored "
+                               "block)" if fused else
+                               "per-GPU iteration: half-step A + half-step B sweeps incl. halo planes (96 B/voxel over "
+                               "the stored block)"),
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": peak_src}
+                    "peak_source": peak_src, "bytes_per_voxel": bpv}
         # ---- end to end through the public sharded API with pinned host buffers ----------------------
         e2e = None
         del sh
@@ -99,7 +107,7 @@ def run_sharded(args):
                 t0 = time.perf_counter()
                 xd = torch.empty(plan.local_shape, dtype=torch.float32, device=dev)
                 xd.copy_(torch.from_numpy(host_in), non_blocking=True)
-                recon, bn, dl = sharded.denoise4D_sharded(xd, mu, iters, True, plan=plan)
+                recon, bn, dl = sharded.denoise4D_sharded(xd, mu, iters, True, plan=plan, schedule=args.schedule)
                 torch.from_numpy(host_out).copy_(recon, non_blocking=True)
                 torch.cuda.synchronize()
                 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -115,8 +123,9 @@ def run_sharded(args):
             line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                     "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                    "config": workload_config(world) if not args.shape else
-                    {"workload": f"4-D FISTA fp32 sharded, {'x'.join(map(str, per))} per GPU (non-default)"},
+                    "config": dict(workload_config(world) if not args.shape else
+                                   {"workload": f"4-D FISTA fp32 sharded, {'x'.join(map(str, per))} per GPU (non-default)"},
+                                   schedule=args.schedule),
                     "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches[0]),
                     "clocks": clk,
                     "check": {"bnorm_last": float(last[0]), "delta_last": float(last[1] / last[2]) if last[2] else None}}

@@ -49,7 +49,7 @@ class DenoiseParams(C.Structure):
         ("clip", C.c_double * 4),
         ("lambda_mu", C.c_double * 4),
         ("device", C.c_int32),
-        ("reserved", C.c_int32),
+        ("schedule", C.c_int32),
         ("stream", C.c_void_p),
     ]
 
@@ -70,6 +70,8 @@ PROTOTYPES = {
                                                 C.c_int, C.c_int, C.c_int, _vp, C.POINTER(StepOpts), _vp]),
     "cytvdn_datacube_update": (C.c_int, [C.c_int, _i64p, C.c_int, _vp, _vp, _vp, _vpp, _dp, C.c_int, _vp,
                                          C.POINTER(StepOpts), _vp]),
+    "cytvdn_fused_iteration": (C.c_int, [C.c_int, _i64p, C.c_int, _vp, _vp, _vp, _vpp, _vpp, _vpp, _vpp, C.c_double,
+                                         _dp, _dp, C.c_int, _vp, C.POINTER(StepOpts), _vp]),
     "cytvdn_sum_square_error": (C.c_int, [C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
     "cytvdn_denoise": (C.c_int, [C.POINTER(DenoiseParams), _vp, _vp, _vp, _dp, _dp, _dp,
                                  C.POINTER(C.c_int32), _dp]),

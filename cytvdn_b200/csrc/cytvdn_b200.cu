@@ -4,6 +4,7 @@
 // (cyTVDN/cyTVDN.py:127-247, :350-435).
 #include "../../include/cytvdn_b200.h"
 #include "kernels.cuh"
+#include "fused.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -375,6 +376,79 @@ int run_sse(int64_t n, const void *a, const void *b, double *out, cudaStream_t s
     return CYTVDN_OK;
 }
 
+// ---- fused iteration ------------------------------------------------------------------------------
+struct FusedCall {
+    Dims D;
+    const void *orig, *uin;
+    void *uout;
+    const void *bin[4], *din[4];     // embedded axis order
+    void *bout[4], *dout[4];
+    double clip[4], w[4];
+    int bc[4];
+    bool fista;
+    double tk;
+    int zero_wrap;
+    double *sums_dev;
+    const cytvdn_step_opts *opts;
+    cudaStream_t st;
+};
+
+template <typename T>
+int run_fused(const FusedCall &c)
+{
+    FusedParams<T> P;
+    memset(&P, 0, sizeof P);
+    bool vec = (c.D.n[3] % vec_width<T>() == 0) && aligned16(c.orig) && aligned16(c.uin) && aligned16(c.uout);
+    int nax = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (c.D.ndim == 3 && k == 2) continue;
+        ++nax;
+        if (!c.bin[k] || !c.bout[k]) return fail(CYTVDN_E_INVALID, "accumulator in/out for axis slot %d is NULL", k);
+        if (c.fista && (!c.din[k] || !c.dout[k])) return fail(CYTVDN_E_INVALID, "FISTA auxiliary in/out for axis slot %d is NULL", k);
+        if (c.bin[k] == c.bout[k] || (c.fista && c.din[k] == c.dout[k]))
+            return fail(CYTVDN_E_INVALID, "the fused iteration is out of place: in and out arrays must differ");
+        vec = vec && aligned16(c.bin[k]) && aligned16(c.bout[k]) &&
+              (!c.fista || (aligned16(c.din[k]) && aligned16(c.dout[k])));
+        P.bin[k] = (const T *)c.bin[k]; P.bout[k] = (T *)c.bout[k];
+        P.din[k] = (const T *)c.din[k]; P.dout[k] = (T *)c.dout[k];
+        P.clip[k] = (T)c.clip[k]; P.w[k] = (T)c.w[k]; P.bc[k] = c.bc[k];
+    }
+    if (c.uin == c.uout) return fail(CYTVDN_E_INVALID, "the fused iteration is out of place: recon_in == recon_out");
+    const int vw = vec ? vec_width<T>() : 1;
+    // every array of the sweep transits L2 and recon must survive 2*TJ planes (read as x+e0, x, x-e0)
+    const int arrays = 3 + nax * (c.fista ? 4 : 2);
+    if (int rc = make_sweep(c.D, vw, sizeof(T), c.opts, 2 * arrays, &P.S)) return rc;
+    P.f = (const T *)c.orig; P.uin = (const T *)c.uin; P.uout = (T *)c.uout;
+    P.tk = (T)c.tk; P.zero_wrap = c.zero_wrap;
+    { const char *env = getenv("CYTVDN_FUSED_HINT"); P.hint = env ? atoi(env) : 0; }
+    Workspace ws;
+    if (int rc = get_workspace(c.st, &ws)) return rc;
+    P.W.partials = ws.partials; P.W.ticket = ws.ticket; P.W.out = c.sums_dev;
+    if (P.S.ntiles <= 0) {
+        CUDA_TRY(cudaMemsetAsync(c.sums_dev, 0, 3 * sizeof(double), c.st));
+        return CYTVDN_OK;
+    }
+    int grid = 1;
+#define LAUNCH_FUSED(VWV, FV, AX2V)                                                    \
+    do {                                                                               \
+        auto k = tv_fused_kernel<T, VWV, FV, AX2V>;                                    \
+        if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;                        \
+        k<<<grid, kBlock, 0, c.st>>>(P);                                               \
+    } while (0)
+    const bool ax2 = c.D.ndim == 4;
+    if (vec) {
+        if (c.fista) { if (ax2) LAUNCH_FUSED(vec_width<T>(), true, true); else LAUNCH_FUSED(vec_width<T>(), true, false); }
+        else         { if (ax2) LAUNCH_FUSED(vec_width<T>(), false, true); else LAUNCH_FUSED(vec_width<T>(), false, false); }
+    } else {
+        if (c.fista) { if (ax2) LAUNCH_FUSED(1, true, true); else LAUNCH_FUSED(1, true, false); }
+        else         { if (ax2) LAUNCH_FUSED(1, false, true); else LAUNCH_FUSED(1, false, false); }
+    }
+#undef LAUNCH_FUSED
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return CYTVDN_OK;
+}
+
 bool is_device_ptr(const void *p)
 {
     cudaPointerAttributes at;
@@ -484,6 +558,34 @@ int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void
                : run_dcu<double>(D, orig, recon_in, recon_out, b, lambda_mu, zw, sums_dev, opts, (cudaStream_t)stream);
 }
 
+int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void *orig, const void *recon_in,
+                           void *recon_out, const void *const *b_in, void *const *b_out, const void *const *d_in,
+                           void *const *d_out, double tk, const double *clip, const double *lambda_mu, int bc_mode,
+                           double *sums_dev, const cytvdn_step_opts *opts, void *stream)
+{
+    FusedCall c;
+    memset(&c, 0, sizeof c);
+    if (int rc = make_dims(ndim, shape, &c.D)) return rc;
+    if (int rc = check_common(dtype, orig, sums_dev)) return rc;
+    if (!recon_in || !recon_out || !b_in || !b_out || !clip || !lambda_mu)
+        return fail(CYTVDN_E_INVALID, "recon / b / clip / lambda_mu is NULL");
+    if ((d_in == nullptr) != (d_out == nullptr)) return fail(CYTVDN_E_INVALID, "d_in and d_out must both be given or both be NULL");
+    if (bc_mode == 1)
+        return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=1 (mirror) is undefined behaviour in the reference's "
+                                          "datacube_update (utils.pyx:117-120) and is not implemented");
+    if (bc_mode != 0 && bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
+    for (int k = 0; k < ndim; ++k) {
+        const int s = c.D.axmap[k];
+        c.bin[s] = b_in[k]; c.bout[s] = b_out[k];
+        c.din[s] = d_in ? d_in[k] : nullptr; c.dout[s] = d_out ? d_out[k] : nullptr;
+        c.clip[s] = clip[k]; c.w[s] = lambda_mu[k]; c.bc[s] = bc_mode;
+        if (opts && ((opts->zero_wrap_mask >> k) & 1)) c.zero_wrap |= 1 << s;
+    }
+    c.orig = orig; c.uin = recon_in; c.uout = recon_out;
+    c.fista = d_in != nullptr; c.tk = tk; c.sums_dev = sums_dev; c.opts = opts; c.st = (cudaStream_t)stream;
+    return dtype == CYTVDN_F32 ? run_fused<float>(c) : run_fused<double>(c);
+}
+
 int cytvdn_sum_square_error(int64_t n, int dtype, const void *a, const void *b, double *sse_dev, void *stream)
 {
     if (int rc = check_common(dtype, a, sse_dev)) return rc;
@@ -537,6 +639,37 @@ static int validate_params(const cytvdn_denoise_params *p, Dims *D)
     return CYTVDN_OK;
 }
 
+namespace {
+// Which schedule a run uses: 2 = fused single pass (76 B/voxel, needs a second set of b/d arrays),
+// 1 = two passes (96 B/voxel, in place).  params->schedule: 0 auto, 1, 2; env CYTVDN_SCHEDULE overrides.
+bool fused_possible(const cytvdn_denoise_params *p)
+{
+    return !p->isotropic_R && !p->isotropic_Q && (p->bc_mode == 0 || p->bc_mode == 2);
+}
+int requested_schedule(const cytvdn_denoise_params *p)
+{
+    int want = p->schedule;
+    const char *env = getenv("CYTVDN_SCHEDULE");
+    if (env && *env) {
+        if (!strcmp(env, "fused") || !strcmp(env, "2")) want = 2;
+        else if (!strcmp(env, "two_pass") || !strcmp(env, "1")) want = 1;
+    }
+    return want;
+}
+int64_t arrays_needed(const cytvdn_denoise_params *p, bool fused, bool data_dev, bool recon_dev, bool ref_host)
+{
+    const int nd = p->ndim;
+    const bool any = p->iters_fista + p->iters_plain > 0;
+    int64_t a = 0;
+    if (any) a += (int64_t)nd * (p->iters_fista > 0 ? 2 : 1) * (fused ? 2 : 1);   // b (+d), ping-pong when fused
+    if (!data_dev) a += 1;
+    if (!recon_dev) a += 1;
+    if (fused && any) a += 1;                                                       // second recon buffer
+    if (ref_host) a += 1;
+    return a;
+}
+}  // namespace
+
 int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *p, int data_on_device, int recon_on_device,
                                    int64_t *bytes)
 {
@@ -544,17 +677,16 @@ int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *p, int data_on_d
     if (int rc = validate_params(p, &D)) return rc;
     if (!bytes) return fail(CYTVDN_E_INVALID, "bytes is NULL");
     const int64_t nb = D.n[0] * D.n[1] * D.n[2] * D.n[3] * (p->dtype == CYTVDN_F32 ? 4 : 8);
-    int64_t arrays = p->ndim + (p->iters_fista > 0 ? p->ndim : 0);
-    if (!data_on_device) arrays += 1;
-    if (!recon_on_device) arrays += 1;
-    *bytes = arrays * nb;
+    const bool fused = fused_possible(p) && requested_schedule(p) != 1;
+    *bytes = arrays_needed(p, fused, data_on_device != 0, recon_on_device != 0, false) * nb;
     return CYTVDN_OK;
 }
 
 namespace {
 struct DevBuf {      // frees on scope exit
     std::vector<void *> ptrs;
-    ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+    ~DevBuf() { release(); }
+    void release() { for (void *p : ptrs) cudaFree(p); ptrs.clear(); }
     int alloc(void **p, size_t bytes)
     {
         cudaError_t e = cudaMalloc(p, bytes);
@@ -590,30 +722,45 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaStream_t st = (cudaStream_t)p->stream;
 
+    // ---- schedule: fused single pass when it applies and the second state set fits ----------------
+    bool fused = false;
+    {
+        const int want = requested_schedule(p);
+        if (want == 2 && !fused_possible(p))
+            return fail(CYTVDN_E_INVALID, "the fused schedule does not cover half-isotropic updates; use schedule 0 or 1");
+        if (want != 1 && fused_possible(p) && nIt > 0) {
+            size_t free_b = 0, tot_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+            const int64_t need = arrays_needed(p, true, data_dev, recon_dev, reference_data && !ref_dev) * (int64_t)nb;
+            fused = want == 2 || need + (int64_t)(512ll << 20) <= (int64_t)free_b;
+        }
+    }
+
     cudaEvent_t ev[4];
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
     struct EvFree { cudaEvent_t *e; ~EvFree() { for (int k = 0; k < 4; ++k) cudaEventDestroy(e[k]); } } evfree{ev};
     CUDA_TRY(cudaEventRecord(ev[0], st));
 
     DevBuf pool;
-    void *b[4] = {0, 0, 0, 0}, *d[4] = {0, 0, 0, 0};
-    void *orig_d = nullptr, *recon_d = nullptr, *ref_d = nullptr;
+    void *b[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, *d[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    void *orig_d = nullptr, *rbuf[2] = {nullptr, nullptr}, *ref_d = nullptr;
     double *sums_d = nullptr;
     if (data_dev) orig_d = const_cast<void *>(data);
     else { if (int rc = pool.alloc(&orig_d, nb)) return rc; CUDA_TRY(cudaMemcpyAsync(orig_d, data, nb, cudaMemcpyHostToDevice, st)); }
-    if (recon_dev) recon_d = recon;
-    else if (int rc = pool.alloc(&recon_d, nb)) return rc;
+    if (recon_dev) rbuf[0] = recon;
+    else if (int rc = pool.alloc(&rbuf[0], nb)) return rc;
+    if (fused) if (int rc = pool.alloc(&rbuf[1], nb)) return rc;
     if (reference_data) {
         if (ref_dev) ref_d = const_cast<void *>(reference_data);
         else { if (int rc = pool.alloc(&ref_d, nb)) return rc; CUDA_TRY(cudaMemcpyAsync(ref_d, reference_data, nb, cudaMemcpyHostToDevice, st)); }
     }
     for (int k = 0; k < nd && nIt > 0; ++k) {
-        if (int rc = pool.alloc(&b[k], nb)) return rc;
-        CUDA_TRY(cudaMemsetAsync(b[k], 0, nb, st));
-        if (nF > 0) {
-            if (int rc = pool.alloc(&d[k], nb)) return rc;
-            CUDA_TRY(cudaMemsetAsync(d[k], 0, nb, st));
+        for (int s = 0; s < (fused ? 2 : 1); ++s) {
+            if (int rc = pool.alloc(&b[s][k], nb)) return rc;
+            if (nF > 0) if (int rc = pool.alloc(&d[s][k], nb)) return rc;
         }
+        CUDA_TRY(cudaMemsetAsync(b[0][k], 0, nb, st));            // only the set that is read first
+        if (nF > 0) CUDA_TRY(cudaMemsetAsync(d[0][k], 0, nb, st));
     }
     // per iteration: [0] sum|b|, [1] sum|delta|, [2] sum|old|, [3] sse ; slot nIt holds MSE[0]
     const size_t nsums = (size_t)(nIt + 1) * 4;
@@ -629,8 +776,10 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
 
     CUDA_TRY(cudaEventRecord(ev[1], st));
     // iteration 0 reads the reconstruction straight from the input (recon = datacube.copy(),
-    // cyTVDN.py:145) and writes recon_d, which saves the device-to-device copy.
+    // cyTVDN.py:145), which saves the device-to-device copy.
     const void *u_cur = orig_d;
+    int cur = 0;                 // fused: state set that holds the current b/d ; recon buffer to write next
+    int rnext = 0;
     double tk = 1.0;
     int done[2] = {0, 0};
     std::vector<char> ran(nIt > 0 ? nIt : 1, 0);
@@ -645,15 +794,26 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
                 tk = tk_new;
             }
             double *s = sums_d + (size_t)i * 4;
-            if (int rc = cytvdn_accumulator_update_all(nd, p->shape, p->dtype, u_cur, b, phase == 0 ? d : nullptr, tkr,
-                                                       p->clip, p->isotropic_R, p->isotropic_Q, p->bc_mode, s, nullptr, st))
-                return rc;
-            if (int rc = cytvdn_datacube_update(nd, p->shape, p->dtype, orig_d, u_cur, recon_d, b, p->lambda_mu,
-                                                p->bc_mode, s + 1, nullptr, st))
-                return rc;
-            u_cur = recon_d;
+            void *u_out = rbuf[rnext];
+            if (fused) {
+                if (int rc = cytvdn_fused_iteration(nd, p->shape, p->dtype, orig_d, u_cur, u_out, b[cur], b[1 - cur],
+                                                    phase == 0 ? d[cur] : nullptr, phase == 0 ? d[1 - cur] : nullptr,
+                                                    tkr, p->clip, p->lambda_mu, p->bc_mode, s, nullptr, st))
+                    return rc;
+                cur = 1 - cur;
+                rnext = 1 - rnext;
+            } else {
+                if (int rc = cytvdn_accumulator_update_all(nd, p->shape, p->dtype, u_cur, b[0], phase == 0 ? d[0] : nullptr,
+                                                           tkr, p->clip, p->isotropic_R, p->isotropic_Q, p->bc_mode, s,
+                                                           nullptr, st))
+                    return rc;
+                if (int rc = cytvdn_datacube_update(nd, p->shape, p->dtype, orig_d, u_cur, u_out, b[0], p->lambda_mu,
+                                                    p->bc_mode, s + 1, nullptr, st))
+                    return rc;
+            }
+            u_cur = u_out;
             if (reference_data)
-                if (int rc = cytvdn_sum_square_error(nvox, p->dtype, ref_d, recon_d, s + 3, st)) return rc;
+                if (int rc = cytvdn_sum_square_error(nvox, p->dtype, ref_d, u_cur, s + 3, st)) return rc;
             ran[i] = 1;
             ++done[phase];
             if (p->use_stopping) {                              // cyTVDN.py:189-194 / :236-242
@@ -665,11 +825,11 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
             }
         }
     }
-    if (nIt == 0 || u_cur == orig_d)
-        CUDA_TRY(cudaMemcpyAsync(recon_d, orig_d, nb, cudaMemcpyDeviceToDevice, st));
+    if (u_cur != rbuf[0])                      // zero iterations, or the fused ping-pong ended in the spare buffer
+        CUDA_TRY(cudaMemcpyAsync(rbuf[0], u_cur, nb, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaEventRecord(ev[2], st));
 
-    if (!recon_dev) CUDA_TRY(cudaMemcpyAsync(recon, recon_d, nb, cudaMemcpyDeviceToHost, st));
+    if (!recon_dev) CUDA_TRY(cudaMemcpyAsync(recon, rbuf[0], nb, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(sums_h.data(), sums_d, nsums * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < nIt; ++i) {
@@ -678,9 +838,8 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         if (mse) mse[i + 1] = ran[i] ? sums_h[(size_t)i * 4 + 3] : 0.0;
     }
     if (mse) mse[0] = sums_h[(size_t)nIt * 4 + 3];
-    if (iters_done) { iters_done[0] = done[0]; iters_done[1] = done[1]; }
-    for (void *q : pool.ptrs) cudaFree(q);
-    pool.ptrs.clear();
+    if (iters_done) { iters_done[0] = done[0]; iters_done[1] = done[1]; iters_done[2] = fused ? 2 : 1; }
+    pool.release();
     CUDA_TRY(cudaEventRecord(ev[3], st));
     CUDA_TRY(cudaEventSynchronize(ev[3]));
     if (timing_ms) {

@@ -1,0 +1,200 @@
+// fused.cuh -- one whole TV iteration (half-step A for all axes + half-step B) in ONE pass.
+//
+// Two-pass traffic is 96 B/voxel (4-D FISTA fp32): half-step B re-reads recon and the four
+// accumulators that half-step A just wrote.  Here every tile computes, besides its own b'_d[x],
+// the forward neighbours b'_d[x+e_d] it needs for the divergence from the OLD state (recon, b, d of
+// the neighbouring voxel, all L2 hits in strip order), so each array crosses HBM once:
+//   read  f, recon, b_d, d_d        (1 + 1 + 4 + 4)
+//   write recon', b'_d, d'_d        (1 + 4 + 4)            = 19 elements = 76 B/voxel.
+// Because neighbours are recomputed from the old state, the new state goes to a second set of
+// arrays (ping-pong); nothing is updated in place and tiles are independent of each other.
+// Per-voxel arithmetic is the reference's, operation for operation, so the
+// result is bit-identical to running the two separate half-steps.
+#pragma once
+#include "kernels.cuh"
+
+namespace cytvdn {
+
+template <typename T>
+struct FusedParams {
+    Sweep S;
+    const T *f;
+    const T *uin;
+    T *uout;
+    const T *bin[4];
+    T *bout[4];
+    const T *din[4];
+    T *dout[4];
+    T clip[4];
+    T w[4];
+    T tk;
+    int32_t bc[4];        // 0 periodic, 2 Jia-Zhao (mirror is undefined for half-step B)
+    int32_t zero_wrap;    // bit k: b'_k beyond the last index of axis k is 0 (sharded upper edge)
+    int32_t hint;         // experiment knob (CYTVDN_FUSED_HINT): cache policies of the loads
+    RedWork W;            // out[0] = sum|b'|, out[1] = sum|recon' - recon|, out[2] = sum|recon|
+};
+
+// v = clip((u - p) + b);  b' = v + tk (v - d)   (anisotropic.pyx:46-54, :127-132)
+template <typename T, bool FISTA>
+__device__ __forceinline__ void acc_update(T u, T p, T b, T d, T clip, T tk, T &v, T &bn)
+{
+    v = clipval((u - p) + b, clip);
+    bn = FISTA ? (v + tk * (v - d)) : v;
+}
+
+template <typename T, int VW, bool FISTA, bool AX2>
+#ifndef FUSED_MINB
+#define FUSED_MINB 2
+#endif
+__global__ void __launch_bounds__(kBlock, FUSED_MINB)
+tv_fused_kernel(const FusedParams<T> P)
+{
+    const Sweep &S = P.S;
+    const int lane = threadIdx.x & 31;
+    // hint bit0: last-use ("self") loads evict-first in L2; bit1: ... and not allocated in L1;
+    //      bit2: neighbour loads evict-last in L2
+    const uint64_t pol = (P.hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t poln = (P.hint & 4) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const bool na = (P.hint & 2) != 0;
+    auto ld_self = [&](const T *p) -> Vec<T, VW> {
+        return na ? ld_ro_stream<T, VW>(p, pol) : ld_ro_hint<T, VW>(p, pol);
+    };
+    auto ld_nbr = [&](const T *p) -> Vec<T, VW> { return ld_ro_hint<T, VW>(p, poln); };
+    double acc[3] = {0.0, 0.0, 0.0};
+    constexpr int NFAR = AX2 ? 3 : 2;                 // far axes 0, 1 (, 2)
+
+    for (int32_t t = blockIdx.x; t < S.ntiles; t += gridDim.x) {
+        // Inactive threads (tail of a slab) run on valid addresses of the slab start and only skip the
+        // stores and the sums: no divergence before the loads, so all of them are issued back to back.
+        const Coord c = locate<VW>(S, t);
+        const int64_t e = c.e;
+        const int32_t coord[3] = {c.i, c.j, c.k};
+        const int32_t extent[3] = {S.n0, S.n1, S.n2};
+        const int64_t stride[3] = {S.st0, S.st1, (int64_t)S.n3};
+
+        // ---------------- addresses (selects, no branches) -----------------------------------------
+        int64_t poff[3], yoff[3];
+        bool at_end[3];
+#pragma unroll
+        for (int d = 0; d < NFAR; ++d) {
+            const int64_t span = (int64_t)(extent[d] - 1) * stride[d];
+            // backward neighbour; at index 0: itself (Jia-Zhao, difference 0) or the last index (periodic)
+            poff[d] = coord[d] != 0 ? e - stride[d] : (P.bc[d] == 2 ? e : e + span);
+            at_end[d] = coord[d] == extent[d] - 1;
+            yoff[d] = at_end[d] ? e - span : e + stride[d];          // forward neighbour (wraps to index 0)
+            if ((P.hint >> (8 + d)) & 1) yoff[d] = e;                // DEBUG knob: no forward neighbour on axis d
+            if ((P.hint >> (12 + d)) & 1) poff[d] = e;               // DEBUG knob: no backward neighbour on axis d
+        }
+
+        // ---------------- phase 1: this thread's own voxels (first touch of every line: HBM) ----------
+        const Vec<T, VW> us = ld_nbr(P.uin + e);
+        const Vec<T, VW> f = ld_self(P.f + e);
+        const Vec<T, VW> b3 = ld_self(P.bin[3] + e);
+        Vec<T, VW> d3;
+        if (FISTA) d3 = ld_self(P.din[3] + e);
+        Vec<T, VW> pv[3], bs[3], ds[3], uy[3], by[3], dy[3];
+#pragma unroll
+        for (int d = 0; d < NFAR; ++d) {
+            bs[d] = ld_self(P.bin[d] + e);                            // last use of these lines
+            if (FISTA) ds[d] = ld_self(P.din[d] + e);
+        }
+        // fast axis (3): neighbours live in adjacent lanes.  The shuffle consumes `us`, i.e. the warp
+        // waits here until its own lines have arrived ...
+        T left = __shfl_up_sync(0xffffffffu, us.v[VW - 1], 1);
+        // ---------------- phase 2: neighbours, issued one memory latency later -----------------------
+        // ... and only then asks for its neighbours' lines.  Those are the phase-1 lines of other warps /
+        // CTAs of the same wave, requested at the same moment as ours: by now they sit in L1/L2.  Asked
+        // for concurrently they would each be fetched from HBM again (measured: L2 hit rate 3 %, DRAM
+        // reads x2) -- neither L1 nor L2 merges a miss into a fill that is still in flight.
+        // The barrier carries a predicate computed from the shuffle result, so it cannot be scheduled
+        // before the shuffle, i.e. before this warp's own lines have arrived.
+        if (__syncthreads_or(left != left) == 0x5a5a5a5a) return;       // never taken (result is 0 or 1)
+#pragma unroll
+        for (int d = 0; d < NFAR; ++d) {
+            pv[d] = ld_ro_ordered<T, VW>(P.uin + poff[d]);
+            uy[d] = ld_ro_ordered<T, VW>(P.uin + yoff[d]);
+            by[d] = ld_ro_ordered<T, VW>(P.bin[d] + yoff[d]);
+            if (FISTA) dy[d] = ld_ro_ordered<T, VW>(P.din[d] + yoff[d]);
+        }
+        if (c.l0 == 0) left = (P.bc[3] == 2) ? us.v[0] : __ldg(P.uin + e + (S.n3 - 1));
+        else if (lane == 0) left = __ldg(P.uin + e - 1);
+        Vec<T, VW> v3, n3s;      // clipped value and new accumulator of this thread's voxels, axis 3
+#pragma unroll
+        for (int v = 0; v < VW; ++v)
+            acc_update<T, FISTA>(us.v[v], v == 0 ? left : us.v[v - 1], b3.v[v], FISTA ? d3.v[v] : T(0),
+                                 P.clip[3], P.tk, v3.v[v], n3s.v[v]);
+        T right3 = __shfl_down_sync(0xffffffffu, n3s.v[0], 1);     // b'_3 of the next voxel on the row
+        if (c.l0 + VW == S.n3) {                                    // row end: wrap to l = 0 (or 0)
+            if (P.zero_wrap & 8) right3 = T(0);
+            else {
+                const int64_t y = e + VW - S.n3;
+                const T uyy = __ldg(P.uin + y);
+                const T py = (P.bc[3] == 2) ? uyy : us.v[VW - 1];
+                T vy;
+                acc_update<T, FISTA>(uyy, py, __ldg(P.bin[3] + y), FISTA ? __ldg(P.din[3] + y) : T(0),
+                                     P.clip[3], P.tk, vy, right3);
+            }
+        } else if (lane == 31) {                                    // next vector belongs to another warp
+            const int64_t y = e + VW;
+            T vy;
+            acc_update<T, FISTA>(__ldg(P.uin + y), us.v[VW - 1], __ldg(P.bin[3] + y),
+                                 FISTA ? __ldg(P.din[3] + y) : T(0), P.clip[3], P.tk, vy, right3);
+        }
+        if (c.active) {
+            st_stream<T, VW>(P.bout[3] + e, n3s);
+            if (FISTA) st_stream<T, VW>(P.dout[3] + e, v3);
+        }
+        T sb = T(0);                       // sum |b'| of this thread's voxels (<= 16 values)
+        Vec<T, VW> term[4];                // w_d (b'_d[x] - b'_d[x+e_d])
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            sb += absval(n3s.v[v]);
+            term[3].v[v] = P.w[3] * (n3s.v[v] - (v == VW - 1 ? right3 : n3s.v[v + 1 < VW ? v + 1 : v]));
+        }
+
+        // ---------------- far axes: b'_d at x (stored) and at x + e_d (recomputed, used only here) ----
+#pragma unroll
+        for (int d = 0; d < NFAR; ++d) {
+            Vec<T, VW> vs, ns;
+            const bool zero = at_end[d] && ((P.zero_wrap >> d) & 1);
+            const bool jz0 = at_end[d] && P.bc[d] == 2;      // neighbour sits at index 0: difference is 0
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                acc_update<T, FISTA>(us.v[v], pv[d].v[v], bs[d].v[v], FISTA ? ds[d].v[v] : T(0), P.clip[d], P.tk,
+                                     vs.v[v], ns.v[v]);
+                T vy, nf;
+                acc_update<T, FISTA>(uy[d].v[v], jz0 ? uy[d].v[v] : us.v[v], by[d].v[v], FISTA ? dy[d].v[v] : T(0),
+                                     P.clip[d], P.tk, vy, nf);
+                if (zero) nf = T(0);
+                sb += absval(ns.v[v]);
+                term[d].v[v] = P.w[d] * (ns.v[v] - nf);
+            }
+            if (c.active) {
+                st_stream<T, VW>(P.bout[d] + e, ns);
+                if (FISTA) st_stream<T, VW>(P.dout[d] + e, vs);
+            }
+        }
+
+        // ---------------- reconstruction update (utils.pyx:96-104) --------------------------------
+        Vec<T, VW> un;
+        T sd = T(0), so = T(0);
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            T s = term[0].v[v] + term[1].v[v];
+            if (AX2) s = s + term[2].v[v];
+            s = s + term[3].v[v];
+            un.v[v] = f.v[v] - s;
+            sd += absval(un.v[v] - us.v[v]);
+            so += absval(us.v[v]);
+        }
+        if (c.active) st_stream<T, VW>(P.uout + e, un);
+        if (c.owned) {
+            acc[0] += (double)sb;
+            acc[1] += (double)sd;
+            acc[2] += (double)so;
+        }
+    }
+    reduce_finish<3>(acc, P.W);
+}
+
+}  // namespace cytvdn

@@ -166,6 +166,38 @@ class ShardPlan:
         rest = _complement(n, first + skip)
         return first, rest
 
+    # ---- fused schedule (one pass per iteration): only the reconstruction travels, both ways ----
+    def after_fused(self) -> List[HaloOp]:
+        """After a fused iteration the new reconstruction's first owned plane goes left and its last
+        owned plane goes right; the overlap planes are received.  (Accumulators never travel: the
+        forward neighbour b'[last owned + 1] is recomputed locally from the overlap plane's state.)"""
+        ops = []
+        for k in range(2):
+            n = self.local_shape[k]
+            if self.has_lo[k]:
+                ops.append(HaloOp("send", "recon", k, 1, self.peer(k, -1)))
+                ops.append(HaloOp("recv", "recon", k, 0, self.peer(k, -1)))
+            if self.has_hi[k]:
+                ops.append(HaloOp("send", "recon", k, n - 2, self.peer(k, +1)))
+                ops.append(HaloOp("recv", "recon", k, n - 1, self.peer(k, +1)))
+        return ops
+
+    def fused_boxes(self):
+        """(halo-first, rest) axis-0 ranges of a fused iteration.  First: the planes that are sent and
+        the upper overlap plane (its garbage recon must be written before the receive lands).  The lower
+        overlap plane is never swept: nothing owned depends on its accumulators, its recon is received."""
+        n = self.local_shape[0]
+        first = set()
+        if self.has_lo[0]:
+            first.add(1)
+        if self.has_hi[0]:
+            first.update((n - 2, n - 1))
+        skip = {0} if self.has_lo[0] else set()
+        first -= skip
+        fb = _runs(sorted(first))
+        rest = _complement(n, fb + _runs(sorted(skip)))
+        return fb, rest
+
     def describe(self) -> str:
         return (f"rank {self.rank}/{self.world} tile {self.tile} of grid {self.grid}: owns "
                 f"[{self.valid[0][0]}:{self.valid[0][1]}, {self.valid[1][0]}:{self.valid[1][1]}], "
@@ -180,6 +212,16 @@ def _complement(n, boxes):
         cur = max(cur, hi)
     if cur < n:
         out.append((cur, n))
+    return out
+
+
+def _runs(idx):
+    out = []
+    for i in idx:
+        if out and out[-1][1] == i:
+            out[-1] = (out[-1][0], i + 1)
+        else:
+            out.append((i, i + 1))
     return out
 
 
@@ -229,7 +271,7 @@ class CudaShard:
 
     SLOTS = 16          # doubles of reduction scratch per iteration
 
-    def __init__(self, plan: ShardPlan, shard, mu, lam=None, fista=True, n_iter=1):
+    def __init__(self, plan: ShardPlan, shard, mu, lam=None, fista=True, n_iter=1, fused=False):
         import torch
         from . import _lib
         self.torch, self._lib, self.lib = torch, _lib, _lib.load()
@@ -252,6 +294,38 @@ class CudaShard:
         self.sums = torch.zeros((max(n_iter, 1), self.SLOTS), dtype=torch.float64, device=shard.device)
         self.arrays = {"b0": self.b[0], "b1": self.b[1], "recon": self.recon}
         self.launches = 0
+        self.fused = fused
+        if fused:       # second state set: the fused iteration is out of place (ping-pong)
+            self.recon2 = torch.empty_like(shard)
+            self.b2 = [torch.empty_like(shard) for _ in range(4)]
+            self.d2 = [torch.empty_like(shard) for _ in range(4)] if fista else None
+            self.bp2 = (C.c_void_p * 4)(*[t.data_ptr() for t in self.b2])
+            self.dp2 = (C.c_void_p * 4)(*[t.data_ptr() for t in self.d2]) if fista else None
+            self.first = True       # iteration 0 reads recon == orig
+
+    def fused_step(self, it: int, slot: int, tk_ratio: float, fista: bool, box0=None):
+        """One fused iteration on an axis-0 range: state (recon, b, d) -> (recon2, b2, d2)."""
+        st = self.torch.cuda.current_stream(self.orig.device).cuda_stream
+        out = self.sums.data_ptr() + 8 * (it * self.SLOTS + slot)
+        o = self._opts(box0)
+        self._lib.check(self.lib.cytvdn_fused_iteration(
+            4, self.sh, self.code, self.orig.data_ptr(), self.recon.data_ptr(), self.recon2.data_ptr(),
+            self.bp, self.bp2, self.dp if fista else None, self.dp2 if fista else None, float(tk_ratio),
+            self.clip, self.w, 2, out, C.byref(o), st))
+        self.launches += 1
+
+    def fused_swap(self):
+        """After all boxes of an iteration (and its exchange) the new state becomes the current one."""
+        self.recon, self.recon2 = self.recon2, self.recon
+        self.b, self.b2, self.bp, self.bp2 = self.b2, self.b, self.bp2, self.bp
+        if self.d is not None:
+            self.d, self.d2, self.dp, self.dp2 = self.d2, self.d, self.dp2, self.dp
+        self.arrays = {"b0": self.b[0], "b1": self.b[1], "recon": self.recon}
+
+    def fused_local_sums(self):
+        """Slots of the fused launches: 3 doubles each (sum|b|, sum|delta|, sum|old|), 4 doubles apart."""
+        s = self.sums
+        return self.torch.stack([s[:, 0:16:4].sum(1), s[:, 1:16:4].sum(1), s[:, 2:16:4].sum(1)], dim=1)
 
     def _opts(self, box0=None):
         o = self._lib.StepOpts()
@@ -316,6 +390,43 @@ def _run_iteration_overlapped(sh: CudaShard, it, tkr, fista, group, comm_stream)
             main.wait_stream(comm_stream)
 
 
+def _run_iteration_fused(sh: CudaShard, it, tkr, fista, group, comm_stream):
+    """Fused schedule, 1-D split: planes to send first, one exchange of the NEW reconstruction (both
+    directions) on ``comm_stream`` under the interior sweep, then the state sets swap roles."""
+    torch = sh.torch
+    main = torch.cuda.current_stream(sh.orig.device)
+    plan = sh.plan
+    one_d = plan.grid[1] == 1
+    first, rest = plan.fused_boxes() if one_d else ([], [(0, plan.local_shape[0])])
+    ops = plan.after_fused()
+    slot = 0
+    for box in first:
+        sh.fused_step(it, slot, tkr, fista, box)
+        slot += 4
+    new_arrays = {"recon": sh.recon2}
+    if ops and one_d and comm_stream is not None:
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ev)
+            works, unpack = halo_exchange(ops, new_arrays, group)
+            for w_ in works:
+                w_.wait()
+            unpack()
+    for box in rest:
+        sh.fused_step(it, slot, tkr, fista, box)
+        slot += 4
+    if ops:
+        if one_d and comm_stream is not None:
+            main.wait_stream(comm_stream)
+        else:
+            works, unpack = halo_exchange(ops, new_arrays, group)
+            for w_ in works:
+                w_.wait()
+            unpack()
+    sh.fused_swap()
+
+
 def _run_iteration_simple(sh: CudaShard, it, tkr, fista, group):
     """Any grid: full sweep, then exchange (what `mpi.py` does, minus its barriers)."""
     for phase in ("a", "b"):
@@ -332,13 +443,15 @@ def _run_iteration_simple(sh: CudaShard, it, tkr, fista, group):
 
 
 def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_change=None, *, plan: ShardPlan,
-                      group=None, lam=None, overlap=True, return_state=False):
+                      group=None, lam=None, overlap=True, return_state=False, schedule="fused"):
     """Sharded counterpart of ``denoise4D`` -- call it on every rank of the process group.
 
     ``shard``: this rank's block INCLUDING its overlap planes (``plan.read_global`` of the global
     array), a contiguous CUDA tensor.  Returns ``(recon_local, b_norm, delta_recon)`` where
     ``recon_local[plan.owned_local]`` is this rank's part of the result and the two 1-D arrays are the
     global values (owned-voxel sums, all-reduced).  ``iterations`` may be ``[n_FISTA, n_plain]``.
+    ``schedule``: ``"fused"`` (one pass and one exchange per iteration, needs a second set of
+    accumulator arrays) or ``"two_pass"`` (the reference's structure: two sweeps, two exchanges).
     """
     import torch
     import torch.distributed as dist
@@ -350,7 +463,8 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
         nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
     n = nF + nU
     world = plan.world
-    sh = CudaShard(plan, shard, mu, lam, fista=nF > 0, n_iter=n)
+    fused = schedule == "fused"
+    sh = CudaShard(plan, shard, mu, lam, fista=nF > 0, n_iter=n, fused=fused)
     one_d = plan.grid[1] == 1
     comm_stream = torch.cuda.Stream(device=shard.device) if (overlap and one_d and world > 1) else None
     ran = np.zeros(n, dtype=bool)
@@ -362,13 +476,15 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
             tkr = 0.0
             if phase == 0:
                 tkr, tk = fista_ratio(tk)
-            if comm_stream is not None:
+            if fused:
+                _run_iteration_fused(sh, it, tkr, phase == 0, group, comm_stream)
+            elif comm_stream is not None:
                 _run_iteration_overlapped(sh, it, tkr, phase == 0, group, comm_stream)
             else:
                 _run_iteration_simple(sh, it, tkr, phase == 0, group)
             ran[it] = True
             if stopping_relative_change is not None:          # needs the global delta now
-                s = sh.local_sums()[it].clone()
+                s = (sh.fused_local_sums() if fused else sh.local_sums())[it].clone()
                 if world > 1:
                     dist.all_reduce(s, group=group)
                 glob[it] = s
@@ -378,7 +494,7 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
                 if dl < stopping_relative_change:
                     break
     if stopping_relative_change is None and n > 0:
-        glob = sh.local_sums().clone()
+        glob = (sh.fused_local_sums() if fused else sh.local_sums()).clone()
         if world > 1:
             dist.all_reduce(glob, group=group)
     g = glob.cpu().numpy()
@@ -397,7 +513,8 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
 # schedule -- box order, owned-range reductions, zero-wrap, plane indices -- with the real kernels
 # when fewer GPUs than ranks are available.
 # ------------------------------------------------------------------------------------------------
-def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True, split_boxes=True, lam=None):
+def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True, split_boxes=True, lam=None,
+                          schedule="two_pass"):
     """``gdata``: the GLOBAL array as a CUDA tensor.  Returns (assembled recon, b_norm, delta)."""
     import torch
     if type(iterations) in (list, tuple):
@@ -406,8 +523,22 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
         nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
     n = nF + nU
     plans = [ShardPlan(gdata.shape, world, r, grid) for r in range(world)]
-    shards = [CudaShard(p, gdata[p.read_global].contiguous(), mu, lam, fista=nF > 0, n_iter=n) for p in plans]
+    fused = schedule == "fused"
+    shards = [CudaShard(p, gdata[p.read_global].contiguous(), mu, lam, fista=nF > 0, n_iter=n, fused=fused)
+              for p in plans]
     one_d = plans[0].grid[1] == 1
+
+    def exchange_fused():
+        sent = {}
+        for s in shards:
+            for op in s.plan.after_fused():
+                if op.kind == "send":
+                    sent[(s.plan.rank, op.peer, op.axis)] = plane(s.recon2, op.axis, op.index).clone()
+        for s in shards:
+            for op in s.plan.after_fused():
+                if op.kind == "recv":
+                    plane(s.recon2, op.axis, op.index).copy_(sent.pop((op.peer, s.plan.rank, op.axis)))
+        assert not sent
 
     def exchange(phase):
         sent = {}
@@ -428,6 +559,28 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
             tkr = 0.0
             if phase_f == 0:
                 tkr, tk = fista_ratio(tk)
+            if fused:
+                slots = {}
+                for s in shards:
+                    first, _ = s.plan.fused_boxes() if (split_boxes and one_d) else ([], None)
+                    slot = 0
+                    for box in first:
+                        s.fused_step(it, slot, tkr, phase_f == 0, box)
+                        slot += 4
+                    slots[s.plan.rank] = slot
+                if split_boxes and one_d:
+                    exchange_fused()       # in the real schedule this runs under the "rest" sweep
+                for s in shards:
+                    rest = s.plan.fused_boxes()[1] if (split_boxes and one_d) else [(0, s.plan.local_shape[0])]
+                    slot = slots[s.plan.rank]
+                    for box in rest:
+                        s.fused_step(it, slot, tkr, phase_f == 0, box)
+                        slot += 4
+                if not (split_boxes and one_d):
+                    exchange_fused()
+                for s in shards:
+                    s.fused_swap()
+                continue
             for phase in ("a", "b"):
                 if split_boxes and one_d:
                     slots = {}
@@ -453,7 +606,7 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
     tot = torch.zeros((max(n, 1), 3), dtype=torch.float64, device=gdata.device)
     for s in shards:
         out[s.plan.owned_global] = s.recon[s.plan.owned_local]
-        tot += s.local_sums()
+        tot += s.fused_local_sums() if fused else s.local_sums()
     g = tot.cpu().numpy()
     with np.errstate(all="ignore"):
         return out, g[:n, 0].copy(), (g[:n, 1] / g[:n, 2]).copy()

@@ -312,7 +312,7 @@ def _as_host_vector(x, name):
 
 
 def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, isotropic_R, isotropic_Q,
-             reference_data, BC_mode, lam, quiet, out, timing):
+             reference_data, BC_mode, lam, quiet, out, timing, schedule=None):
     lib = _lib.load()
     torch_in = _is_torch(datacube)
     dt = _np_dtype(datacube)
@@ -368,6 +368,7 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
     P.use_stopping = int(stopping_relative_change is not None)
     P.stopping_relative_change = float(stopping_relative_change) if stopping_relative_change is not None else 0.0
     P.device = -1
+    P.schedule = {None: 0, "auto": 0, "two_pass": 1, "fused": 2}[schedule]
     P.stream = None
 
     device = None
@@ -409,14 +410,14 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
     bn = (C.c_double * max(n, 1))()
     dl = (C.c_double * max(n, 1))()
     ms = (C.c_double * (n + 1))()
-    done = (C.c_int32 * 2)()
+    done = (C.c_int32 * 3)()
     tm = (C.c_double * 3)()
     with _on_device(device):
         check(lib.cytvdn_denoise(C.byref(P), _vp(data_p), _vp(recon_p), _vp(ref_p), bn, dl,
                                  ms if reference_data is not None else None, done, tm))
     if timing is not None:
         timing.update(setup_ms=tm[0], loop_ms=tm[1], finish_ms=tm[2], iters_fista=int(done[0]),
-                      iters_plain=int(done[1]))
+                      iters_plain=int(done[1]), schedule={1: "two_pass", 2: "fused"}.get(int(done[2]), "none"))
     with np.errstate(all="ignore"):
         b_norm = np.array(bn[:n], dtype=np.float64).astype(dt)
         delta_recon = np.array(dl[:n], dtype=np.float64).astype(dt)
@@ -430,7 +431,8 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
 
 
 def denoise4D(datacube, mu, iterations=10, FISTA=True, stopping_relative_change=None, isotropic_R=False,
-              isotropic_Q=False, reference_data=None, BC_mode=2, lam=None, quiet=False, *, out=None, timing=None):
+              isotropic_Q=False, reference_data=None, BC_mode=2, lam=None, quiet=False, *, out=None, timing=None,
+              schedule=None):
     """Proximal (an)isotropic TV denoising of a 4-D datacube on the GPU.
 
     Drop-in for ``cyTVDN.denoise4D`` (`cyTVDN/cyTVDN.py:19-247`): same arguments in the same order,
@@ -439,18 +441,21 @@ def denoise4D(datacube, mu, iterations=10, FISTA=True, stopping_relative_change=
     n_unaccelerated]``.  ``BC_mode=1`` raises (undefined behaviour in the reference).
 
     Extras (keyword only): ``out`` -- array/tensor that receives ``recon`` (e.g. ``pinned_empty``);
-    ``timing`` -- dict filled with setup/loop/finish milliseconds measured with CUDA events.
+    ``timing`` -- dict filled with setup/loop/finish milliseconds measured with CUDA events;
+    ``schedule`` -- ``"fused"`` (one pass per iteration, 76 B/voxel, needs a second set of accumulator
+    arrays), ``"two_pass"`` (96 B/voxel, in place) or ``None``: fused when it applies and fits in memory.
+    All schedules give bit-identical results.
     """
     return _denoise(4, datacube, mu, iterations, FISTA, stopping_relative_change, isotropic_R, isotropic_Q,
-                    reference_data, BC_mode, lam, quiet, out, timing)
+                    reference_data, BC_mode, lam, quiet, out, timing, schedule)
 
 
 def denoise3D(datacube, mu, iterations=7_500, stopping_relative_change=None, BC_mode=2, FISTA=False,
-              reference_data=None, lam=None, quiet=False, *, out=None, timing=None):
+              reference_data=None, lam=None, quiet=False, *, out=None, timing=None, schedule=None):
     """Drop-in for ``cyTVDN.denoise3D`` (`cyTVDN/cyTVDN.py:250-435`).  Note the positional order
     differs from ``denoise4D`` exactly as in the reference."""
     return _denoise(3, datacube, mu, iterations, FISTA, stopping_relative_change, False, False,
-                    reference_data, BC_mode, lam, quiet, out, timing)
+                    reference_data, BC_mode, lam, quiet, out, timing, schedule)
 
 
 def check_memory(datacube):

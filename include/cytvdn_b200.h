@@ -122,6 +122,21 @@ int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void
                            const double *lambda_mu, int bc_mode, double *sums_dev,
                            const cytvdn_step_opts *opts, void *stream);
 
+/*
+ * One WHOLE iteration in a single pass: half-step A for all axes fused with half-step B
+ * (= cytvdn_accumulator_update_all followed by cytvdn_datacube_update, bit-identical results, i.e. the
+ * loop body cyTVDN.py:159-184 / :378-390).  Each array crosses HBM once: 76 B/voxel instead of 96
+ * (4-D FISTA fp32).  OUT OF PLACE: the new state goes to recon_out / b_out / d_out, which must not
+ * alias the inputs (forward neighbours are recomputed from the old state).  Anisotropic only;
+ * bc_mode 0 or 2.  d_in == d_out == NULL -> unaccelerated.
+ * sums_dev[0] = sum |b_new| over all axes, [1] = sum |recon_out - recon_in|, [2] = sum |recon_in|.
+ */
+int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void *orig,
+                           const void *recon_in, void *recon_out, const void *const *b_in,
+                           void *const *b_out, const void *const *d_in, void *const *d_out,
+                           double tk, const double *clip, const double *lambda_mu, int bc_mode,
+                           double *sums_dev, const cytvdn_step_opts *opts, void *stream);
+
 /* sum (a-b)^2 over n elements.  Replaces sum_square_error_4D utils.pyx:14-30, _3D :35-49. */
 int cytvdn_sum_square_error(int64_t n, int dtype, const void *a, const void *b,
                             double *sse_dev, void *stream);
@@ -144,7 +159,8 @@ typedef struct cytvdn_denoise_params {
     double  clip[4];            /* lambdaInv = 1/lam  (cyTVDN.py:77) */
     double  lambda_mu[4];       /* lam/mu             (cyTVDN.py:78) */
     int32_t device;             /* device to run on when `data` is a host pointer; -1 = current */
-    int32_t reserved;
+    int32_t schedule;           /* 0 auto, 1 two passes per iteration (in place), 2 fused single pass
+                                   (out of place, second set of b/d arrays; anisotropic only) */
     void   *stream;             /* NULL = default stream */
 } cytvdn_denoise_params;
 
@@ -153,7 +169,8 @@ typedef struct cytvdn_denoise_params {
  * recon receives the result.  bnorm / delta: HOST arrays of iters_fista + iters_plain doubles
  * (entries of iterations that did not run stay 0, like the reference's trailing zeros);
  * mse: HOST array of that length + 1, or NULL when reference_data is NULL.
- * iters_done[0], iters_done[1]: FISTA / unaccelerated iterations actually executed.
+ * iters_done (3 ints): [0], [1] FISTA / unaccelerated iterations actually executed, [2] the schedule
+ * that ran (1 two-pass, 2 fused).
  * timing_ms (may be NULL): [0] allocation + host->device, [1] iteration loop (CUDA events),
  * [2] device->host + free.
  * The call is synchronous.

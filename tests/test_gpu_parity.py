@@ -122,14 +122,20 @@ def test_step_kernels_match_reference_vectors(tv, steps):
     assert n > 100
 
 
+@pytest.mark.parametrize("schedule", ["two_pass", "fused"])
 @pytest.mark.parametrize("name", DENOISE)
-def test_denoise_matches_reference_driver(tv, name):
+def test_denoise_matches_reference_driver(tv, name, schedule):
     """tv.denoise3D/4D of this package vs the same call on the unmodified reference."""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     meta = INDEX[name]
+    if schedule == "fused" and (meta["kwargs"].get("isotropic_R") or meta["kwargs"].get("isotropic_Q")):
+        pytest.skip("the fused schedule covers the anisotropic update only")
     fn = tv.denoise4D if meta["ndim"] == 4 else tv.denoise3D
     data = z["data"].copy()
-    out = fn(data, z["mu"], quiet=True, **_kwargs(z, meta))
+    tm = {}
+    out = fn(data, z["mu"], quiet=True, schedule=schedule, timing=tm, **_kwargs(z, meta))
+    if np.count_nonzero(z["delta_recon"]) or z["delta_recon"].size:
+        assert tm["schedule"] == schedule
     assert np.array_equal(data, z["data"]), "input was modified"
     recon = out[0]
     assert isinstance(recon, np.ndarray) and recon.dtype == z["recon"].dtype and recon.shape == z["recon"].shape
@@ -173,8 +179,10 @@ CASES_4D = [
 ]
 
 
+@pytest.mark.parametrize("schedule", ["two_pass", "fused"])
 @pytest.mark.parametrize("shape,dt,kw,budget", CASES_4D)
-def test_denoise4d_vs_oracle(tv, O, shape, dt, kw, budget, monkeypatch):
+def test_denoise4d_vs_oracle(tv, O, shape, dt, kw, budget, schedule, monkeypatch):
+    monkeypatch.setenv("CYTVDN_SCHEDULE", schedule)
     if budget is not None:
         monkeypatch.setenv("CYTVDN_L2_BUDGET_MB", str(budget))
     rng = np.random.default_rng(abs(hash((shape, dt))) % 2**32)
@@ -198,8 +206,10 @@ CASES_3D = [
 ]
 
 
+@pytest.mark.parametrize("schedule", ["two_pass", "fused"])
 @pytest.mark.parametrize("shape,dt,kw,budget", CASES_3D)
-def test_denoise3d_vs_oracle(tv, O, shape, dt, kw, budget, monkeypatch):
+def test_denoise3d_vs_oracle(tv, O, shape, dt, kw, budget, schedule, monkeypatch):
+    monkeypatch.setenv("CYTVDN_SCHEDULE", schedule)
     if budget is not None:
         monkeypatch.setenv("CYTVDN_L2_BUDGET_MB", str(budget))
     rng = np.random.default_rng(abs(hash((shape, dt))) % 2**32)
@@ -230,7 +240,9 @@ def test_half_isotropic_vs_oracle(tv, O, dt, flags, fista):
     np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR)
 
 
-def test_early_stop_and_hybrid_semantics(tv, O):
+@pytest.mark.parametrize("schedule", ["two_pass", "fused"])
+def test_early_stop_and_hybrid_semantics(tv, O, schedule, monkeypatch):
+    monkeypatch.setenv("CYTVDN_SCHEDULE", schedule)
     rng = np.random.default_rng(3)
     data = counts(rng, (8, 8, 8, 16), "float32")
     mu = np.array([1, 1, .5, .5], dtype=np.float32)
@@ -445,6 +457,25 @@ def test_sharded_schedule_equals_single_gpu(tv, world, grid, split, iters):
     np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
 
 
+@pytest.mark.parametrize("world,grid,split", [(2, None, True), (3, None, True), (4, None, True), (4, None, False),
+                                               (2, (1, 2), False), (4, (2, 2), False), (6, (3, 2), False)])
+@pytest.mark.parametrize("iters", [12, [5, 4]])
+def test_sharded_fused_schedule_equals_single_gpu(tv, world, grid, split, iters):
+    """Fused schedule: one exchange of the new reconstruction (both directions) per iteration."""
+    import torch
+    from cytvdn_b200 import sharded
+    rng = np.random.default_rng(200 + world)
+    gshape = (13, 14, 8, 16)
+    data = counts(rng, gshape, "float32")
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = tv.denoise4D(data, mu, iters, True, quiet=True, schedule="two_pass")
+    got, bn, dl = sharded.emulate_on_one_device(torch.from_numpy(data).cuda(), mu, world, grid, iters, True, split,
+                                                schedule="fused")
+    assert np.array_equal(got.cpu().numpy(), ref[0])
+    np.testing.assert_allclose(bn, ref[1].astype(np.float64), rtol=1e-5)
+    np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
+
+
 def test_sharded_generator_is_shard_invariant(tv):
     """The device generator yields the same global array whatever the sharding, and equals its
     NumPy mirror bit for bit (so the CPU reference can consume the identical input)."""
@@ -456,3 +487,45 @@ def test_sharded_generator_is_shard_invariant(tv):
     assert np.array_equal(np.concatenate(parts), whole)
     assert np.array_equal(whole, synth.stem4d_hash_numpy(g, seed=7, counts=300.0))
     assert whole.max() > 200 and whole.min() >= 0 and np.all(whole == np.rint(whole))
+
+
+def test_fullsize_fused_iteration_equals_two_pass(tv):
+    """Config-3 size: two FISTA iterations through cytvdn_fused_iteration (out of place, ping-pong) give
+    bit-identical recon / b / d and the same sums as half-step A followed by half-step B."""
+    import ctypes as C
+    import torch
+    from cytvdn_b200 import _lib
+    lib = _lib.load()
+    shape = (256, 256, 128, 128)
+    x = _synth(shape)
+    sh = (C.c_int64 * 4)(*shape)
+    st = torch.cuda.current_stream().cuda_stream
+    clip = (C.c_double * 4)(32.0, 32.0, 64.0, 64.0)
+    w = (C.c_double * 4)(*[1 / 32.0] * 4)
+    ptrs = lambda ts: (C.c_void_p * 4)(*[t.data_ptr() for t in ts])
+    # two-pass, in place
+    b = [torch.zeros_like(x) for _ in range(4)]
+    d = [torch.zeros_like(x) for _ in range(4)]
+    u = x.clone()
+    s2 = torch.zeros((2, 4), dtype=torch.float64, device="cuda")
+    for it, tk in enumerate((0.0, 0.28)):
+        _lib.check(lib.cytvdn_accumulator_update_all(4, sh, 0, u.data_ptr(), ptrs(b), ptrs(d), tk, clip, 0, 0, 2,
+                                                     s2[it].data_ptr(), None, st))
+        _lib.check(lib.cytvdn_datacube_update(4, sh, 0, x.data_ptr(), u.data_ptr(), u.data_ptr(), ptrs(b), w, 2,
+                                              s2[it].data_ptr() + 8, None, st))
+    # fused, ping-pong (iteration 0 reads recon from the input itself)
+    B = [[torch.zeros_like(x) for _ in range(4)], [torch.empty_like(x) for _ in range(4)]]
+    D = [[torch.zeros_like(x) for _ in range(4)], [torch.empty_like(x) for _ in range(4)]]
+    R = [torch.empty_like(x), torch.empty_like(x)]
+    sf = torch.zeros((2, 4), dtype=torch.float64, device="cuda")
+    uin = x
+    for it, tk in enumerate((0.0, 0.28)):
+        _lib.check(lib.cytvdn_fused_iteration(4, sh, 0, x.data_ptr(), uin.data_ptr(), R[it].data_ptr(), ptrs(B[it]),
+                                              ptrs(B[1 - it]), ptrs(D[it]), ptrs(D[1 - it]), tk, clip, w, 2,
+                                              sf[it].data_ptr(), None, st))
+        uin = R[it]
+    torch.cuda.synchronize()
+    assert torch.equal(R[1], u)
+    for k in range(4):
+        assert torch.equal(B[0][k], b[k]) and torch.equal(D[0][k], d[k])
+    np.testing.assert_allclose(sf.cpu().numpy()[:, :3], s2.cpu().numpy()[:, :3], rtol=1e-7)   # fp32 partials of <=16 values
