@@ -28,7 +28,7 @@ class StepOpts(C.Structure):
         ("own_lo", C.c_int64 * 2),
         ("own_hi", C.c_int64 * 2),
         ("zero_wrap_mask", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
         ("l2_budget_bytes", C.c_int64),
     ]
 

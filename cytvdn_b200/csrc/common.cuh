@@ -48,6 +48,7 @@ struct Sweep {
     int32_t tiles_full;        // ni * cps_full
     int32_t ntiles;
     int32_t oi0, oi1, oj0, oj1;// voxels with i in [oi0,oi1) and j in [oj0,oj1) enter the reductions
+    int32_t dynamic;           // 1: tiles are drawn from a global counter, 0: static stride gridDim.x
     FastDiv d_tiles_full, d_cps_full, d_cps_last, d_mv, d_n3v;
 };
 
@@ -275,8 +276,37 @@ __device__ __forceinline__ void st_plain(T *p, const Vec<T, VW> &x)
 // ---- reductions: per-thread float64, warp shuffle, block smem, last-block fixed-order sum -------
 struct RedWork {
     double *partials;     // [grid][NR]
-    unsigned *ticket;     // zero between launches
+    unsigned *ticket;     // [0] arrival ticket of the reduction, [1] tile counter; both zero between launches
     double *out;          // [NR] device
+};
+
+// Tile scheduler of the persistent sweeps.  Static mode: CTA c takes tiles c, c+G, c+2G, ... (no
+// synchronisation; right when the kernel has the GPU to itself).  Dynamic mode (cytvdn_step_opts.flags
+// bit 0): tiles are handed out in sweep order from one global counter, so the CTAs that are resident share
+// all the work -- a sweep that co-runs with NCCL's send/recv CTAs during the halo exchange is not left
+// waiting for CTAs that could not be placed.  The next index is requested at the start of a tile and
+// published at its end (latency hidden).
+struct TileSched {
+    unsigned *counter;
+    int32_t dynamic;
+    int32_t next;         // thread 0 only
+    __device__ __forceinline__ int32_t first() const { return (int32_t)blockIdx.x; }
+    __device__ __forceinline__ void prefetch()
+    {
+        if (dynamic && threadIdx.x == 0) next = (int32_t)(gridDim.x + atomicAdd(counter, 1u));
+    }
+    // all threads; in dynamic mode it contains one barrier.  `body_has_barrier`: the sweep body executes a
+    // block barrier between two calls (else one is added here to protect the shared slot).
+    template <bool body_has_barrier>
+    __device__ __forceinline__ int32_t advance(int32_t t)
+    {
+        if (!dynamic) return t + (int32_t)gridDim.x;
+        __shared__ int32_t s_next;
+        if (!body_has_barrier) __syncthreads();
+        if (threadIdx.x == 0) s_next = next;
+        __syncthreads();
+        return s_next;
+    }
 };
 
 template <int NR>
@@ -327,7 +357,8 @@ __device__ __forceinline__ void reduce_finish(double (&acc)[NR], const RedWork &
             for (int w = 0; w < kWarps; ++w) x += sm[w][r];
             W.out[r] = x;
         }
-        *W.ticket = 0;
+        W.ticket[0] = 0;
+        W.ticket[1] = 0;          // every CTA has drawn its last tile index before it got here
     }
 }
 

@@ -184,6 +184,7 @@ int make_sweep(const Dims &D, int vw, size_t elem, const cytvdn_step_opts *o, in
                             (long long)lo[k], (long long)hi[k], (long long)D.n[k]);
         }
     }
+    S->dynamic = (o && (o->flags & 1)) ? 1 : 0;
     S->i0 = (int32_t)lo[0]; S->ni = (int32_t)(hi[0] - lo[0]);
     S->j0 = (int32_t)lo[1];
     const int64_t nj = hi[1] - lo[1];
@@ -420,7 +421,6 @@ int run_fused(const FusedCall &c)
     if (int rc = make_sweep(c.D, vw, sizeof(T), c.opts, 2 * arrays, &P.S)) return rc;
     P.f = (const T *)c.orig; P.uin = (const T *)c.uin; P.uout = (T *)c.uout;
     P.tk = (T)c.tk; P.zero_wrap = c.zero_wrap;
-    { const char *env = getenv("CYTVDN_FUSED_HINT"); P.hint = env ? atoi(env) : 0; }
     Workspace ws;
     if (int rc = get_workspace(c.st, &ws)) return rc;
     P.W.partials = ws.partials; P.W.ticket = ws.ticket; P.W.out = c.sums_dev;
@@ -683,18 +683,31 @@ int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *p, int data_on_d
 }
 
 namespace {
-struct DevBuf {      // frees on scope exit
-    std::vector<void *> ptrs;
-    ~DevBuf() { release(); }
-    void release() { for (void *p : ptrs) cudaFree(p); ptrs.clear(); }
-    int alloc(void **p, size_t bytes)
+// All device state of one cytvdn_denoise call lives in ONE allocation that is carved up: on B200 twenty
+// 4 GiB cudaMalloc/cudaFree pairs cost ~250 ms, one 80 GiB pair ~35 ms (tools/alloc_timing.py).
+struct Arena {
+    char *base = nullptr;
+    size_t size = 0, used = 0;
+    ~Arena() { release(); }
+    void release() { if (base) cudaFree(base); base = nullptr; size = used = 0; }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+    int reserve(size_t bytes)
     {
-        cudaError_t e = cudaMalloc(p, bytes);
+        cudaError_t e = cudaMalloc((void **)&base, bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
+            base = nullptr;
             return fail(CYTVDN_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         }
-        ptrs.push_back(*p);
+        size = bytes;
+        return CYTVDN_OK;
+    }
+    int alloc(void **p, size_t bytes)
+    {
+        const size_t need = padded(bytes);
+        if (used + need > size) return fail(CYTVDN_E_NOMEM, "internal: arena exhausted (%zu + %zu > %zu)", used, need, size);
+        *p = base + used;
+        used += need;
         return CYTVDN_OK;
     }
 };
@@ -741,7 +754,13 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     struct EvFree { cudaEvent_t *e; ~EvFree() { for (int k = 0; k < 4; ++k) cudaEventDestroy(e[k]); } } evfree{ev};
     CUDA_TRY(cudaEventRecord(ev[0], st));
 
-    DevBuf pool;
+    const size_t nsums = (size_t)(nIt + 1) * 4;
+    Arena pool;
+    {
+        const int64_t arrays = arrays_needed(p, fused, data_dev, recon_dev, reference_data && !ref_dev);
+        if (int rc = pool.reserve((size_t)arrays * Arena::padded(nb) + Arena::padded(nsums * sizeof(double)) + 4096))
+            return rc;
+    }
     void *b[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, *d[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     void *orig_d = nullptr, *rbuf[2] = {nullptr, nullptr}, *ref_d = nullptr;
     double *sums_d = nullptr;
@@ -763,7 +782,6 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         if (nF > 0) CUDA_TRY(cudaMemsetAsync(d[0][k], 0, nb, st));
     }
     // per iteration: [0] sum|b|, [1] sum|delta|, [2] sum|old|, [3] sse ; slot nIt holds MSE[0]
-    const size_t nsums = (size_t)(nIt + 1) * 4;
     if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
     CUDA_TRY(cudaMemsetAsync(sums_d, 0, nsums * sizeof(double), st));
     std::vector<double> sums_h(nsums, 0.0);
@@ -839,9 +857,9 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     }
     if (mse) mse[0] = sums_h[(size_t)nIt * 4 + 3];
     if (iters_done) { iters_done[0] = done[0]; iters_done[1] = done[1]; iters_done[2] = fused ? 2 : 1; }
-    pool.release();
     CUDA_TRY(cudaEventRecord(ev[3], st));
     CUDA_TRY(cudaEventSynchronize(ev[3]));
+    pool.release();
     if (timing_ms) {
         float t = 0;
         CUDA_TRY(cudaEventElapsedTime(&t, ev[0], ev[1])); timing_ms[0] = t;

@@ -30,7 +30,6 @@ struct FusedParams {
     T tk;
     int32_t bc[4];        // 0 periodic, 2 Jia-Zhao (mirror is undefined for half-step B)
     int32_t zero_wrap;    // bit k: b'_k beyond the last index of axis k is 0 (sharded upper edge)
-    int32_t hint;         // experiment knob (CYTVDN_FUSED_HINT): cache policies of the loads
     RedWork W;            // out[0] = sum|b'|, out[1] = sum|recon' - recon|, out[2] = sum|recon|
 };
 
@@ -51,19 +50,15 @@ tv_fused_kernel(const FusedParams<T> P)
 {
     const Sweep &S = P.S;
     const int lane = threadIdx.x & 31;
-    // hint bit0: last-use ("self") loads evict-first in L2; bit1: ... and not allocated in L1;
-    //      bit2: neighbour loads evict-last in L2
-    const uint64_t pol = (P.hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
-    const uint64_t poln = (P.hint & 4) ? l2_policy_evict_last() : l2_policy_evict_normal();
-    const bool na = (P.hint & 2) != 0;
-    auto ld_self = [&](const T *p) -> Vec<T, VW> {
-        return na ? ld_ro_stream<T, VW>(p, pol) : ld_ro_hint<T, VW>(p, pol);
-    };
-    auto ld_nbr = [&](const T *p) -> Vec<T, VW> { return ld_ro_hint<T, VW>(p, poln); };
+    // All reads keep the default L2 policy: marking the last-use ("self") loads evict-first was measured
+    // 25 % slower -- inside a wave a neighbour may still need the line.
+    auto ld_self = [&](const T *p) -> Vec<T, VW> { return ld_ro<T, VW>(p); };
     double acc[3] = {0.0, 0.0, 0.0};
     constexpr int NFAR = AX2 ? 3 : 2;                 // far axes 0, 1 (, 2)
 
-    for (int32_t t = blockIdx.x; t < S.ntiles; t += gridDim.x) {
+    TileSched sched{P.W.ticket + 1, S.dynamic, 0};
+    for (int32_t t = sched.first(); t < S.ntiles; t = sched.template advance<true>(t)) {
+        sched.prefetch();
         // Inactive threads (tail of a slab) run on valid addresses of the slab start and only skip the
         // stores and the sums: no divergence before the loads, so all of them are issued back to back.
         const Coord c = locate<VW>(S, t);
@@ -82,12 +77,10 @@ tv_fused_kernel(const FusedParams<T> P)
             poff[d] = coord[d] != 0 ? e - stride[d] : (P.bc[d] == 2 ? e : e + span);
             at_end[d] = coord[d] == extent[d] - 1;
             yoff[d] = at_end[d] ? e - span : e + stride[d];          // forward neighbour (wraps to index 0)
-            if ((P.hint >> (8 + d)) & 1) yoff[d] = e;                // DEBUG knob: no forward neighbour on axis d
-            if ((P.hint >> (12 + d)) & 1) poff[d] = e;               // DEBUG knob: no backward neighbour on axis d
         }
 
         // ---------------- phase 1: this thread's own voxels (first touch of every line: HBM) ----------
-        const Vec<T, VW> us = ld_nbr(P.uin + e);
+        const Vec<T, VW> us = ld_self(P.uin + e);
         const Vec<T, VW> f = ld_self(P.f + e);
         const Vec<T, VW> b3 = ld_self(P.bin[3] + e);
         Vec<T, VW> d3;

@@ -303,11 +303,11 @@ class CudaShard:
             self.dp2 = (C.c_void_p * 4)(*[t.data_ptr() for t in self.d2]) if fista else None
             self.first = True       # iteration 0 reads recon == orig
 
-    def fused_step(self, it: int, slot: int, tk_ratio: float, fista: bool, box0=None):
+    def fused_step(self, it: int, slot: int, tk_ratio: float, fista: bool, box0=None, dynamic=False):
         """One fused iteration on an axis-0 range: state (recon, b, d) -> (recon2, b2, d2)."""
         st = self.torch.cuda.current_stream(self.orig.device).cuda_stream
         out = self.sums.data_ptr() + 8 * (it * self.SLOTS + slot)
-        o = self._opts(box0)
+        o = self._opts(box0, dynamic)
         self._lib.check(self.lib.cytvdn_fused_iteration(
             4, self.sh, self.code, self.orig.data_ptr(), self.recon.data_ptr(), self.recon2.data_ptr(),
             self.bp, self.bp2, self.dp if fista else None, self.dp2 if fista else None, float(tk_ratio),
@@ -327,8 +327,9 @@ class CudaShard:
         s = self.sums
         return self.torch.stack([s[:, 0:16:4].sum(1), s[:, 1:16:4].sum(1), s[:, 2:16:4].sum(1)], dim=1)
 
-    def _opts(self, box0=None):
+    def _opts(self, box0=None, dynamic=False):
         o = self._lib.StepOpts()
+        o.flags = 1 if dynamic else 0
         n0 = self.plan.local_shape[0]
         o.box_lo[0], o.box_hi[0] = (0, n0) if box0 is None else box0
         o.box_lo[1], o.box_hi[1] = 0, 0
@@ -337,19 +338,19 @@ class CudaShard:
         o.zero_wrap_mask = self.plan.zero_wrap_mask
         return o
 
-    def half_step_a(self, it: int, slot: int, tk_ratio: float, fista: bool, box0=None):
+    def half_step_a(self, it: int, slot: int, tk_ratio: float, fista: bool, box0=None, dynamic=False):
         st = self.torch.cuda.current_stream(self.orig.device).cuda_stream
         out = self.sums.data_ptr() + 8 * (it * self.SLOTS + slot)
-        o = self._opts(box0)
+        o = self._opts(box0, dynamic)
         self._lib.check(self.lib.cytvdn_accumulator_update_all(
             4, self.sh, self.code, self.recon.data_ptr(), self.bp, self.dp if fista else None, float(tk_ratio),
             self.clip, 0, 0, 2, out, C.byref(o), st))
         self.launches += 1
 
-    def half_step_b(self, it: int, slot: int, box0=None):
+    def half_step_b(self, it: int, slot: int, box0=None, dynamic=False):
         st = self.torch.cuda.current_stream(self.orig.device).cuda_stream
         out = self.sums.data_ptr() + 8 * (it * self.SLOTS + slot)
-        o = self._opts(box0)
+        o = self._opts(box0, dynamic)
         self._lib.check(self.lib.cytvdn_datacube_update(
             4, self.sh, self.code, self.orig.data_ptr(), self.recon.data_ptr(), self.recon.data_ptr(), self.bp,
             self.w, 2, out, C.byref(o), st))
@@ -383,8 +384,9 @@ def _run_iteration_overlapped(sh: CudaShard, it, tkr, fista, group, comm_stream)
                 for w_ in works:
                     w_.wait()
                 unpack()
-        for box in rest:
-            (sh.half_step_a(it, slot, tkr, fista, box) if phase == "a" else sh.half_step_b(it, slot, box))
+        for box in rest:          # co-runs with the exchange: dynamic tile scheduling
+            (sh.half_step_a(it, slot, tkr, fista, box, bool(ops)) if phase == "a"
+             else sh.half_step_b(it, slot, box, bool(ops)))
             slot += step
         if ops:
             main.wait_stream(comm_stream)
@@ -413,8 +415,8 @@ def _run_iteration_fused(sh: CudaShard, it, tkr, fista, group, comm_stream):
             for w_ in works:
                 w_.wait()
             unpack()
-    for box in rest:
-        sh.fused_step(it, slot, tkr, fista, box)
+    for box in rest:              # co-runs with the exchange: dynamic tile scheduling
+        sh.fused_step(it, slot, tkr, fista, box, bool(ops) and one_d and comm_stream is not None)
         slot += 4
     if ops:
         if one_d and comm_stream is not None:

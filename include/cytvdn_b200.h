@@ -60,6 +60,9 @@ int         cytvdn_device_count(int *count);
  *  zero_wrap_mask (reconstruction update only): bit k set -> the forward neighbour of the
  *            last index on axis k is taken as 0 instead of reading index 0 (tile on the
  *            global upper edge that holds a received plane at index 0).
+ *  flags bit 0 : hand the tiles of the sweep out dynamically (one global counter) instead of a static
+ *            stride per CTA.  Use it for a sweep that overlaps with other GPU work (the NCCL halo exchange):
+ *            the CTAs that are resident then share all tiles.  ~2 % slower when the kernel runs alone.
  *  l2_budget_bytes : working-set budget that sizes the axis-1 strips of the sweep
  *            (0 = library default).
  */
@@ -69,7 +72,7 @@ typedef struct cytvdn_step_opts {
     int64_t own_lo[2];
     int64_t own_hi[2];
     int32_t zero_wrap_mask;
-    int32_t reserved;
+    int32_t flags;              /* bit 0: dynamic tile scheduling (see below) */
     int64_t l2_budget_bytes;
 } cytvdn_step_opts;
 
