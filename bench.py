@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A *step* is one TV iteration (fused half-step A over all axes + half-step B) over the whole array.
+A *step* is one TV iteration over the whole array: by default ONE fused kernel (half-step A for all axes +
+half-step B, 76 B/voxel); ``--schedule two_pass`` runs the two half-step kernels (96 B/voxel).
 
 N = 1  : BASELINE config 3 -- denoise4D anisotropic FISTA, fp32, 256x256x128x128, mu=[1,1,.5,.5].
 N > 1  : BASELINE config 5 shape, weak scaling: every GPU owns 128x1024x128x128 of a
@@ -13,7 +14,8 @@ N > 1  : BASELINE config 5 shape, weak scaling: every GPU owns 128x1024x128x128 
 One JSON line on rank 0.  ``value`` = voxels x K / device time of the K timed iterations (inputs
 resident in HBM), ``e2e`` = the same metric through the public API ``tv.denoise4D`` with pinned HOST
 buffers (H2D of the data and D2H of the result inside the timed region, 100 iterations as the config
-says), ``roofline`` = the dominant kernel (half-step A) against the measured HBM copy bandwidth,
+says), ``roofline`` = the dominant kernel (the fused iteration kernel, or half-step A with --schedule two_pass)
+against the measured HBM copy bandwidth,
 ``cpu_baseline`` = the unmodified reference kernels (oracle/_ref) timed on this box's host cores on a
 bounded sample.  ``--impl reference`` times only that CPU implementation.
 """
@@ -213,8 +215,8 @@ def run_single(args):
     fused = args.schedule == "fused"
     x = synth.stem4d_device(shape, seed=2, counts=500.0)
     nset = 2 if fused else 1
-    # Arrays of exactly 2^32 bytes allocated back to back alias in the L1/L2 sets (every array has the
-    # same address bits below 2^32); skew the k-th array by k * SKEW bytes like cytvdn_denoise does.
+    # --skew: offset the k-th state array by k * SKEW bytes (experiment: power-of-two array sizes showed no
+    # set-aliasing penalty on B200, default 0)
     skew_elems = args.skew // 4
     counter = [0]
 
@@ -367,7 +369,7 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=100)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--skew", type=int, default=1118976, help="byte skew between consecutive state arrays (N=1 arm)")
+    ap.add_argument("--skew", type=int, default=0, help="byte skew between consecutive state arrays (experiment knob)")
     ap.add_argument("--schedule", default="fused", choices=["fused", "two_pass"],
                     help="fused: one pass per iteration (76 B/voxel); two_pass: half-steps A and B (96 B/voxel)")
     args = ap.parse_args()
