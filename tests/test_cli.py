@@ -1,0 +1,62 @@
+"""The cyTVMPI-style command line (cytvdn_b200/cli.py): flags of mpi.py:47-76, block I/O on .npy files."""
+import os
+
+import numpy as np
+import pytest
+
+from cytvdn_b200 import cli
+from cytvdn_b200.sharded import ShardPlan
+
+
+def test_parser_accepts_the_reference_flags():
+    a = cli.build_parser().parse_args("-i in.npy -o out.npy -d 4 -f 1 -n 40 -L .03 .03 .015 .015 -m 1 1 .5 .5 -v 0".split())
+    assert a.dimensions == [4] and a.fista == [True] and a.niterations == [40] and a.verbose is False
+    assert a.lam == [.03, .03, .015, .015] and a.mu == [1, 1, .5, .5]
+    assert os.path.isabs(a.input[0]) and os.path.isabs(a.output[0])
+    a = cli.build_parser().parse_args("-i a.npy -o b.npy -d 4 -n 10 5 -L 1 1 1 1 -m 1 1 1 1".split())
+    assert a.niterations == [10, 5] and a.fista == [False]          # two counts -> hybrid (FISTA first)
+    with pytest.raises(SystemExit):
+        cli.build_parser().parse_args("-o b.npy -d 4 -n 1 -L 1 -m 1".split())
+
+
+def test_block_io_roundtrip(tmp_path):
+    """Every rank reads its overlapped block and writes its owned block: together they rebuild the file."""
+    rng = np.random.default_rng(0)
+    g = rng.integers(0, 500, (11, 7, 4, 6)).astype(np.uint16)            # counts on disk, cast to float32 on read
+    src, dst = str(tmp_path / "in.npy"), str(tmp_path / "out.npy")
+    np.save(src, g)
+    data = cli.open_input(src)
+    cli.create_output(dst, g.shape)
+    for rank in range(3):
+        p = ShardPlan(g.shape, 3, rank)
+        blk = cli.read_block(data, p.read_global)
+        assert blk.dtype == np.float32 and blk.flags["C_CONTIGUOUS"] and blk.shape == p.local_shape
+        cli.write_block(dst, p.owned_global, blk[p.owned_local] + 1)
+    assert np.array_equal(np.load(dst), g.astype(np.float32) + 1)
+    with pytest.raises(SystemExit, match="unsupported input format"):
+        cli.open_input(str(tmp_path / "x.dm4"))
+
+
+@pytest.mark.gpu
+def test_cli_single_gpu_matches_api(tmp_path):
+    import cytvdn_b200 as tv
+    rng = np.random.default_rng(4)
+    g = rng.poisson(rng.uniform(20, 400, (6, 7, 8, 16))).astype(np.float32)
+    src, dst = str(tmp_path / "in.npy"), str(tmp_path / "out.npy")
+    np.save(src, g)
+    mu = np.array([1, 1, .5, .5], np.float32)
+    lam = mu / 32
+    argv = ["-i", src, "-o", dst, "-d", "4", "-f", "1", "-n", "9", "-v", "0", "-L"] + [str(float(v)) for v in lam] + \
+           ["-m"] + [str(float(v)) for v in mu]
+    assert cli.main(argv) == 0
+    ref = tv.denoise4D(g, mu, 9, True, lam=lam, quiet=True)[0]
+    assert np.array_equal(np.load(dst), ref)
+    # 3-D, hybrid iteration counts
+    c = rng.poisson(rng.uniform(20, 400, (6, 7, 32))).astype(np.float32)
+    np.save(src, c)
+    mu3 = np.array([1, 1, .5], np.float32)
+    argv = ["-i", src, "-o", dst, "-d", "3", "-n", "4", "3", "-v", "0", "-L"] + [str(float(v)) for v in mu3 / 16] + \
+           ["-m"] + [str(float(v)) for v in mu3]
+    assert cli.main(argv) == 0
+    ref = tv.denoise3D(c, mu3, [4, 3], lam=mu3 / 16, quiet=True)[0]
+    assert np.array_equal(np.load(dst), ref)
