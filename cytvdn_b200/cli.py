@@ -78,7 +78,7 @@ def open_input(path, dataset=None):
 
 def read_block(data, slices):
     """This rank's block as a contiguous float32 array (`mpi.py:216-239`)."""
-    return np.ascontiguousarray(data[slices], dtype=np.float32)
+    return np.array(data[slices], dtype=np.float32, order="C")       # always a private, writable copy
 
 
 def create_output(path, shape):

@@ -529,7 +529,8 @@ int cytvdn_accumulator_update_all(int ndim, const int64_t *shape, int dtype, con
         const int s = c.D.axmap[k];
         c.b[s] = b[k]; c.d[s] = d ? d[k] : nullptr; c.clip[s] = clip[k];
         const bool iso = (k < 2 && iso_R) || (k >= 2 && iso_Q);
-        c.bc[s] = iso ? 2 : bc_mode;                       // iso_* kernels know Jia-Zhao only
+        const bool force_jz = opts && ((opts->flags >> (8 + k)) & 1);   // split axis of a periodic sharded run
+        c.bc[s] = (iso || force_jz) ? 2 : bc_mode;         // iso_* kernels know Jia-Zhao only
         if (c.bc[s] == 1 && shape[k] < 2) return fail(CYTVDN_E_INVALID, "mirror boundary needs extent >= 2 on axis %d", k);
     }
     c.a = a; c.fista = d != nullptr; c.tk = tk;
@@ -578,7 +579,8 @@ int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void
         const int s = c.D.axmap[k];
         c.bin[s] = b_in[k]; c.bout[s] = b_out[k];
         c.din[s] = d_in ? d_in[k] : nullptr; c.dout[s] = d_out ? d_out[k] : nullptr;
-        c.clip[s] = clip[k]; c.w[s] = lambda_mu[k]; c.bc[s] = bc_mode;
+        c.clip[s] = clip[k]; c.w[s] = lambda_mu[k];
+        c.bc[s] = (opts && ((opts->flags >> (8 + k)) & 1)) ? 2 : bc_mode;
         if (opts && ((opts->zero_wrap_mask >> k) & 1)) c.zero_wrap |= 1 << s;
     }
     c.orig = orig; c.uin = recon_in; c.uout = recon_out;

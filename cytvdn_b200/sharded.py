@@ -19,7 +19,9 @@ Deviations from `mpi.py`, all required for the sharded result to equal the singl
   - FISTA is supported (the reference stops at "haven't done FISTA yet", `mpi.py:310-311`): only the
     accumulators travel, never the auxiliaries;
   - ``b_norm`` / ``delta`` are produced: sums over OWNED voxels, all-reduced (3 doubles / iteration).
-Only ``BC_mode=2`` exists in sharded mode, as in `mpi.py:84`.
+`mpi.py:84` knows ``BC_mode=2`` only; here ``ShardPlan(..., periodic=True)`` adds ``BC_mode=0``: the first and the last
+tile of a split axis exchange planes too and the kernels treat that axis as Jia-Zhao inside the block
+(``cytvdn_step_opts.flags`` bits 8..11), so the wrap is done by the exchange.
 
 Default layout on NVSwitch: 1-D over axis 0 (contiguous halo planes, two neighbours); the halo planes
 are computed first and travel on a side stream while the interior is computed.  The reference's 2-D
@@ -62,12 +64,15 @@ class HaloOp:
     axis: int
     index: int
     peer: int
+    side: str = "lo"    # on which side of this tile the peer sits; a send to "lo" pairs with a receive from "hi"
 
 
 class ShardPlan:
     """Where one rank's block sits in the global array and what it exchanges."""
 
-    def __init__(self, gshape: Sequence[int], world: int, rank: int, grid=None):
+    def __init__(self, gshape: Sequence[int], world: int, rank: int, grid=None, periodic: bool = False):
+        """``periodic``: BC_mode 0 -- the first and the last tile of a split axis are neighbours too (the wrap
+        of that axis is done by the halo exchange; not available in `mpi.py:84`)."""
         gshape = tuple(int(v) for v in gshape)
         assert len(gshape) == 4, "sharding exists for 4-D datacubes only (mpi.py:252-255)"
         if grid is None:
@@ -77,6 +82,7 @@ class ShardPlan:
         wx, wy = int(grid[0]), int(grid[1])
         assert wx * wy == world, f"grid {grid} does not match world size {world}"
         self.gshape, self.world, self.rank, self.grid = gshape, world, rank, (wx, wy)
+        self.periodic = bool(periodic)
         self.tile = (rank // wy, rank % wy)                       # np.unravel_index(rank, (wx, wy)), mpi.py:156
         n = [math.ceil(gshape[0] / wx), math.ceil(gshape[1] / wy)]   # mpi.py:161-162
         self.valid, self.read, self.has_lo, self.has_hi = [], [], [], []
@@ -87,6 +93,8 @@ class ShardPlan:
                 raise ValueError(f"axis {k}: extent {gshape[k]} cannot be split over {w} tiles of {n[k]} planes "
                                  f"(tile {t} would be empty)")
             has_lo, has_hi = t > 0, t < w - 1                      # mpi.py:183-187
+            if self.periodic and w > 1:
+                has_lo = has_hi = True
             self.valid.append((lo, hi))
             self.read.append((lo - 1 if has_lo else lo, hi + 1 if has_hi else hi))   # mpi.py:173-180
             self.has_lo.append(has_lo)
@@ -96,11 +104,35 @@ class ShardPlan:
         self.own_lo = [1 if self.has_lo[k] else 0 for k in range(2)]
         self.own_hi = [self.local_shape[k] - (1 if self.has_hi[k] else 0) for k in range(2)]
 
-    # neighbour ranks (mpi.py:199-210)
+    # neighbour ranks (mpi.py:199-210); they wrap around in a periodic plan
     def peer(self, axis: int, step: int) -> int:
         t = list(self.tile)
-        t[axis] += step
+        t[axis] = (t[axis] + step) % self.grid[axis]
         return t[0] * self.grid[1] + t[1]
+
+    def read_indices(self, axis: int):
+        """Global indices of the stored planes on a scan axis (wrapping in a periodic plan)."""
+        lo, hi = self.read[axis]
+        return [g % self.gshape[axis] for g in range(lo, hi)]
+
+    def extract(self, garray):
+        """This rank's block (owned + overlap planes) of a global NumPy array / torch tensor."""
+        if not self.periodic:
+            return garray[self.read_global]
+        i0, i1 = self.read_indices(0), self.read_indices(1)
+        if isinstance(garray, np.ndarray):
+            return garray[np.ix_(i0, i1)]
+        import torch
+        a = garray.index_select(0, torch.as_tensor(i0, device=garray.device))
+        return a.index_select(1, torch.as_tensor(i1, device=garray.device))
+
+    @property
+    def jz_flags(self) -> int:
+        """cytvdn_step_opts.flags bits 8+k: split axes of a periodic run use the Jia-Zhao boundary inside
+        the block (their wrap is the exchange's job)."""
+        if not self.periodic:
+            return 0
+        return sum(1 << (8 + k) for k in range(2) if self.grid[k] > 1)
 
     @property
     def owned_local(self):
@@ -122,6 +154,8 @@ class ShardPlan:
     @property
     def zero_wrap_mask(self) -> int:
         """Axes on which this tile ends at the global upper edge but holds a received plane 0."""
+        if self.periodic:
+            return 0
         return sum(1 << k for k in range(2) if self.has_lo[k] and not self.has_hi[k])
 
     def after_a(self) -> List[HaloOp]:
@@ -129,9 +163,9 @@ class ShardPlan:
         ops = []
         for k in range(2):
             if self.has_hi[k]:
-                ops.append(HaloOp("send", f"b{k}", k, self.local_shape[k] - 2, self.peer(k, +1)))
+                ops.append(HaloOp("send", f"b{k}", k, self.local_shape[k] - 2, self.peer(k, +1), "hi"))
             if self.has_lo[k]:
-                ops.append(HaloOp("recv", f"b{k}", k, 0, self.peer(k, -1)))
+                ops.append(HaloOp("recv", f"b{k}", k, 0, self.peer(k, -1), "lo"))
         return ops
 
     def after_b(self) -> List[HaloOp]:
@@ -139,9 +173,9 @@ class ShardPlan:
         ops = []
         for k in range(2):
             if self.has_lo[k]:
-                ops.append(HaloOp("send", "recon", k, 1, self.peer(k, -1)))
+                ops.append(HaloOp("send", "recon", k, 1, self.peer(k, -1), "lo"))
             if self.has_hi[k]:
-                ops.append(HaloOp("recv", "recon", k, self.local_shape[k] - 1, self.peer(k, +1)))
+                ops.append(HaloOp("recv", "recon", k, self.local_shape[k] - 1, self.peer(k, +1), "hi"))
         return ops
 
     # sweep boxes (axis-0 ranges) for the overlapped 1-D schedule
@@ -172,14 +206,18 @@ class ShardPlan:
         owned plane goes right; the overlap planes are received.  (Accumulators never travel: the
         forward neighbour b'[last owned + 1] is recomputed locally from the overlap plane's state.)"""
         ops = []
+        # Order matters when both neighbours are the same rank (2 tiles on a periodic axis): NCCL pairs the
+        # sends and receives of two ranks in posting order, so sends go lo, hi and receives hi, lo.
         for k in range(2):
             n = self.local_shape[k]
             if self.has_lo[k]:
-                ops.append(HaloOp("send", "recon", k, 1, self.peer(k, -1)))
-                ops.append(HaloOp("recv", "recon", k, 0, self.peer(k, -1)))
+                ops.append(HaloOp("send", "recon", k, 1, self.peer(k, -1), "lo"))
             if self.has_hi[k]:
-                ops.append(HaloOp("send", "recon", k, n - 2, self.peer(k, +1)))
-                ops.append(HaloOp("recv", "recon", k, n - 1, self.peer(k, +1)))
+                ops.append(HaloOp("send", "recon", k, n - 2, self.peer(k, +1), "hi"))
+            if self.has_hi[k]:
+                ops.append(HaloOp("recv", "recon", k, n - 1, self.peer(k, +1), "hi"))
+            if self.has_lo[k]:
+                ops.append(HaloOp("recv", "recon", k, 0, self.peer(k, -1), "lo"))
         return ops
 
     def fused_boxes(self):
@@ -272,6 +310,7 @@ class CudaShard:
     SLOTS = 16          # doubles of reduction scratch per iteration
 
     def __init__(self, plan: ShardPlan, shard, mu, lam=None, fista=True, n_iter=1, fused=False):
+        self.bc_mode = 0 if plan.periodic else 2
         import torch
         from . import _lib
         self.torch, self._lib, self.lib = torch, _lib, _lib.load()
@@ -311,7 +350,7 @@ class CudaShard:
         self._lib.check(self.lib.cytvdn_fused_iteration(
             4, self.sh, self.code, self.orig.data_ptr(), self.recon.data_ptr(), self.recon2.data_ptr(),
             self.bp, self.bp2, self.dp if fista else None, self.dp2 if fista else None, float(tk_ratio),
-            self.clip, self.w, 2, out, C.byref(o), st))
+            self.clip, self.w, self.bc_mode, out, C.byref(o), st))
         self.launches += 1
 
     def fused_swap(self):
@@ -329,7 +368,7 @@ class CudaShard:
 
     def _opts(self, box0=None, dynamic=False):
         o = self._lib.StepOpts()
-        o.flags = 1 if dynamic else 0
+        o.flags = (1 if dynamic else 0) | self.plan.jz_flags
         n0 = self.plan.local_shape[0]
         o.box_lo[0], o.box_hi[0] = (0, n0) if box0 is None else box0
         o.box_lo[1], o.box_hi[1] = 0, 0
@@ -344,7 +383,7 @@ class CudaShard:
         o = self._opts(box0, dynamic)
         self._lib.check(self.lib.cytvdn_accumulator_update_all(
             4, self.sh, self.code, self.recon.data_ptr(), self.bp, self.dp if fista else None, float(tk_ratio),
-            self.clip, 0, 0, 2, out, C.byref(o), st))
+            self.clip, 0, 0, self.bc_mode, out, C.byref(o), st))
         self.launches += 1
 
     def half_step_b(self, it: int, slot: int, box0=None, dynamic=False):
@@ -353,7 +392,7 @@ class CudaShard:
         o = self._opts(box0, dynamic)
         self._lib.check(self.lib.cytvdn_datacube_update(
             4, self.sh, self.code, self.orig.data_ptr(), self.recon.data_ptr(), self.recon.data_ptr(), self.bp,
-            self.w, 2, out, C.byref(o), st))
+            self.w, self.bc_mode, out, C.byref(o), st))
         self.launches += 1
 
     # slot layout per iteration: A launches 0..3 (1 double each), B launches 4.. (2 doubles each)
@@ -454,6 +493,7 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
     global values (owned-voxel sums, all-reduced).  ``iterations`` may be ``[n_FISTA, n_plain]``.
     ``schedule``: ``"fused"`` (one pass and one exchange per iteration, needs a second set of
     accumulator arrays) or ``"two_pass"`` (the reference's structure: two sweeps, two exchanges).
+    Boundary: Jia-Zhao (``BC_mode=2``) or, with a ``ShardPlan(..., periodic=True)``, periodic (``BC_mode=0``).
     """
     import torch
     import torch.distributed as dist
@@ -516,7 +556,7 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
 # when fewer GPUs than ranks are available.
 # ------------------------------------------------------------------------------------------------
 def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True, split_boxes=True, lam=None,
-                          schedule="two_pass"):
+                          schedule="two_pass", periodic=False):
     """``gdata``: the GLOBAL array as a CUDA tensor.  Returns (assembled recon, b_norm, delta)."""
     import torch
     if type(iterations) in (list, tuple):
@@ -524,9 +564,9 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
     else:
         nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
     n = nF + nU
-    plans = [ShardPlan(gdata.shape, world, r, grid) for r in range(world)]
+    plans = [ShardPlan(gdata.shape, world, r, grid, periodic) for r in range(world)]
     fused = schedule == "fused"
-    shards = [CudaShard(p, gdata[p.read_global].contiguous(), mu, lam, fista=nF > 0, n_iter=n, fused=fused)
+    shards = [CudaShard(p, p.extract(gdata).contiguous(), mu, lam, fista=nF > 0, n_iter=n, fused=fused)
               for p in plans]
     one_d = plans[0].grid[1] == 1
 
@@ -535,11 +575,12 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
         for s in shards:
             for op in s.plan.after_fused():
                 if op.kind == "send":
-                    sent[(s.plan.rank, op.peer, op.axis)] = plane(s.recon2, op.axis, op.index).clone()
+                    sent[(s.plan.rank, op.peer, op.axis, op.side)] = plane(s.recon2, op.axis, op.index).clone()
         for s in shards:
             for op in s.plan.after_fused():
                 if op.kind == "recv":
-                    plane(s.recon2, op.axis, op.index).copy_(sent.pop((op.peer, s.plan.rank, op.axis)))
+                    other = "hi" if op.side == "lo" else "lo"
+                    plane(s.recon2, op.axis, op.index).copy_(sent.pop((op.peer, s.plan.rank, op.axis, other)))
         assert not sent
 
     def exchange(phase):
@@ -547,11 +588,12 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
         for s in shards:
             for op in (s.plan.after_a() if phase == "a" else s.plan.after_b()):
                 if op.kind == "send":
-                    sent[(s.plan.rank, op.peer, op.array, op.axis)] = plane(s.arrays[op.array], op.axis, op.index).clone()
+                    sent[(s.plan.rank, op.peer, op.array, op.axis, op.side)] = plane(s.arrays[op.array], op.axis, op.index).clone()
         for s in shards:
             for op in (s.plan.after_a() if phase == "a" else s.plan.after_b()):
                 if op.kind == "recv":
-                    plane(s.arrays[op.array], op.axis, op.index).copy_(sent.pop((op.peer, s.plan.rank, op.array, op.axis)))
+                    other = "hi" if op.side == "lo" else "lo"
+                    plane(s.arrays[op.array], op.axis, op.index).copy_(sent.pop((op.peer, s.plan.rank, op.array, op.axis, other)))
         assert not sent
 
     tk = 1.0

@@ -63,6 +63,9 @@ int         cytvdn_device_count(int *count);
  *  flags bit 0 : hand the tiles of the sweep out dynamically (one global counter) instead of a static
  *            stride per CTA.  Use it for a sweep that overlaps with other GPU work (the NCCL halo exchange):
  *            the CTAs that are resident then share all tiles.  ~2 % slower when the kernel runs alone.
+ *  flags bits 8..11 : axis k (bit 8+k) uses the Jia-Zhao boundary in the accumulator update whatever
+ *            bc_mode says.  For periodic runs that are split on axis k: the wrap there is done by the halo
+ *            exchange, the block's own index 0 on that axis is an overlap plane.
  *  l2_budget_bytes : working-set budget that sizes the axis-1 strips of the sweep
  *            (0 = library default).
  */
@@ -72,7 +75,7 @@ typedef struct cytvdn_step_opts {
     int64_t own_lo[2];
     int64_t own_hi[2];
     int32_t zero_wrap_mask;
-    int32_t flags;              /* bit 0: dynamic tile scheduling (see below) */
+    int32_t flags;              /* bit 0: dynamic tile scheduling, bits 8..11: per-axis Jia-Zhao (see below) */
     int64_t l2_budget_bytes;
 } cytvdn_step_opts;
 

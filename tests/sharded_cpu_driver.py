@@ -28,7 +28,9 @@ class CpuShard:
 
     def half_step_a(self, tkr, fista):
         for ax in range(4):
-            self.K.accumulator_update(self.recon, self.b[ax], self.d[ax] if fista else None, tkr, ax, self.clip[ax], 2)
+            # periodic plan: axes that are split use Jia-Zhao inside the block, the others wrap locally
+            bc = 0 if (self.plan.periodic and not (ax < 2 and self.plan.grid[ax] > 1)) else 2
+            self.K.accumulator_update(self.recon, self.b[ax], self.d[ax] if fista else None, tkr, ax, self.clip[ax], bc)
         return float(sum(np.abs(self._own(x), dtype=np.float64).sum() for x in self.b))
 
     def half_step_b(self):
@@ -67,19 +69,20 @@ def apply_ops_in_process(shards, phase):
         ops = sh.plan.after_a() if phase == "a" else sh.plan.after_b()
         for op in ops:
             if op.kind == "send":
-                sends[(sh.plan.rank, op.peer, op.array, op.axis)] = plane(sh.arrays[op.array], op.axis, op.index).copy()
+                sends[(sh.plan.rank, op.peer, op.array, op.axis, op.side)] = plane(sh.arrays[op.array], op.axis, op.index).copy()
     for sh in shards:
         ops = sh.plan.after_a() if phase == "a" else sh.plan.after_b()
         for op in ops:
             if op.kind == "recv":
-                plane(sh.arrays[op.array], op.axis, op.index)[...] = sends.pop((op.peer, sh.plan.rank, op.array, op.axis))
+                other = "hi" if op.side == "lo" else "lo"
+                plane(sh.arrays[op.array], op.axis, op.index)[...] = sends.pop((op.peer, sh.plan.rank, op.array, op.axis, other))
     assert not sends, "unmatched sends"
 
 
-def run_in_process(gdata, mu, world, grid, n_fista, n_plain, K):
+def run_in_process(gdata, mu, world, grid, n_fista, n_plain, K, periodic=False):
     """All ranks in one process.  Returns (assembled recon, b_norm, delta)."""
-    plans = [ShardPlan(gdata.shape, world, r, grid) for r in range(world)]
-    shards = [CpuShard(p, np.ascontiguousarray(gdata[p.read_global]), mu, K, fista=n_fista > 0) for p in plans]
+    plans = [ShardPlan(gdata.shape, world, r, grid, periodic) for r in range(world)]
+    shards = [CpuShard(p, np.ascontiguousarray(p.extract(gdata)), mu, K, fista=n_fista > 0) for p in plans]
     bn, dl = [], []
     tk = 1.0
     for phase, cnt in ((0, n_fista), (1, n_plain)):

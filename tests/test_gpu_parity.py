@@ -476,6 +476,24 @@ def test_sharded_fused_schedule_equals_single_gpu(tv, world, grid, split, iters)
     np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
 
 
+@pytest.mark.parametrize("schedule", ["two_pass", "fused"])
+@pytest.mark.parametrize("world,grid,split", [(2, None, True), (3, None, True), (4, None, False), (2, (1, 2), False),
+                                               (4, (2, 2), False), (6, (2, 3), False)])
+def test_sharded_periodic_equals_single_gpu(tv, world, grid, split, schedule):
+    """BC_mode=0 sharded: wrap-around exchange between the first and the last tile."""
+    import torch
+    from cytvdn_b200 import sharded
+    rng = np.random.default_rng(300 + world)
+    data = counts(rng, (13, 14, 8, 16), "float32")
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = tv.denoise4D(data, mu, [6, 4], True, BC_mode=0, quiet=True, schedule="two_pass")
+    got, bn, dl = sharded.emulate_on_one_device(torch.from_numpy(data).cuda(), mu, world, grid, [6, 4], True, split,
+                                                schedule=schedule, periodic=True)
+    assert np.array_equal(got.cpu().numpy(), ref[0])
+    np.testing.assert_allclose(bn, ref[1].astype(np.float64), rtol=1e-5)
+    np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
+
+
 def test_sharded_generator_is_shard_invariant(tv):
     """The device generator yields the same global array whatever the sharding, and equals its
     NumPy mirror bit for bit (so the CPU reference can consume the identical input)."""

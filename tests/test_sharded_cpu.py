@@ -153,3 +153,34 @@ def test_gloo_world2_halo_exchange(grid):
         assert np.array_equal(got, ref[0])
         np.testing.assert_allclose(sums[:, 0], ref[1], rtol=1e-12)
         np.testing.assert_allclose(sums[:, 1] / sums[:, 2], ref[2], rtol=1e-10)
+
+
+@pytest.mark.parametrize("world,grid", [(1, None), (2, None), (3, None), (4, None), (2, (1, 2)), (4, (2, 2)), (6, (3, 2)), (6, (2, 3))])
+@pytest.mark.parametrize("fista", [True, False])
+def test_periodic_in_process_emulation_equals_single_process(world, grid, fista):
+    """BC_mode=0 sharded: the first and last tile of a split axis are neighbours, the split axes use the
+    Jia-Zhao boundary inside the block, the exchange does the wrap.  Two tiles on an axis = both neighbours are the
+    same rank."""
+    O.set_threads(O.max_threads())
+    rng = np.random.default_rng(40 + world)
+    data = counts(rng, (13, 10, 6, 5))
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    K = O.PortKernels("D")
+    n = 12
+    ref = O.denoise4D(data, mu, n, fista, BC_mode=0, quiet=True, kernels=K, scalars="D")
+    got, bn, dl = drv.run_in_process(data, mu, world, grid, n if fista else 0, 0 if fista else n, K, periodic=True)
+    assert np.array_equal(got, ref[0]), f"max diff {np.abs(got - ref[0]).max()}"
+    np.testing.assert_allclose(bn, ref[1], rtol=1e-12)
+    np.testing.assert_allclose(dl, ref[2], rtol=1e-10)
+
+
+def test_periodic_plan_wraps():
+    p0 = ShardPlan((12, 10, 3, 4), 3, 0, None, periodic=True)
+    p2 = ShardPlan((12, 10, 3, 4), 3, 2, None, periodic=True)
+    assert p0.has_lo[0] and p0.has_hi[0] and p0.peer(0, -1) == 2 and p2.peer(0, +1) == 0
+    assert p0.read_indices(0) == [11, 0, 1, 2, 3, 4] and p2.read_indices(0) == [7, 8, 9, 10, 11, 0]
+    assert p0.zero_wrap_mask == 0 and p0.jz_flags == 1 << 8 and not p0.has_lo[1]
+    g = np.arange(12 * 10 * 3 * 4, dtype=np.float32).reshape(12, 10, 3, 4)
+    assert np.array_equal(p0.extract(g), g[[11, 0, 1, 2, 3, 4]])
+    one = ShardPlan((12, 10, 3, 4), 1, 0, None, periodic=True)
+    assert not one.has_lo[0] and one.jz_flags == 0 and one.local_shape == (12, 10, 3, 4)

@@ -33,29 +33,33 @@ def main():
     try:
         mu = np.array([1, 1, .5, .5], dtype=np.float32)
         cases = []
-        for grid in (None, "mpi"):
-            for sched in ("fused", "two_pass"):
-                for iters, stop in ((25, None), ([8, 5], None), (60, 0.002)):
-                    cases.append((grid, sched, iters, stop))
-        for grid, sched, iters, stop in cases:
-            gshape = (8 * world + 3, 12, 32, 64)           # uneven split on axis 0
-            plan = sharded.ShardPlan(gshape, world, rank, grid)
+        grids = [None] + ([(2, world // 2)] if world % 2 == 0 and world >= 4 else [])
+        for periodic in (False, True):
+            for grid in grids:
+                for sched in ("fused", "two_pass"):
+                    for iters, stop in ((25, None), ([8, 5], None), (60, 0.002)):
+                        cases.append((grid, sched, iters, stop, periodic))
+        for grid, sched, iters, stop, periodic in cases:
+            gshape = (8 * world + 3, 13, 32, 64)           # uneven splits
+            plan = sharded.ShardPlan(gshape, world, rank, grid, periodic)
             whole = synth.stem4d_device(gshape, seed=11, counts=400.0, device=dev)
-            shard = whole[plan.read_global].contiguous()
+            shard = plan.extract(whole).contiguous()
             recon, bn, dl = sharded.denoise4D_sharded(shard, mu, iters, True, stop, plan=plan, schedule=sched)
             # gather the owned blocks on rank 0
             out = torch.zeros(gshape, dtype=torch.float32, device=dev)
             out[plan.owned_global] = recon[plan.owned_local]
             dist.all_reduce(out)                            # blocks are disjoint: the sum is the assembly
             if rank == 0:
-                ref = tv.denoise4D(whole, mu, iters, True, stop, quiet=True, schedule="two_pass")
+                ref = tv.denoise4D(whole, mu, iters, True, stop, BC_mode=0 if periodic else 2, quiet=True,
+                                   schedule="two_pass")
                 same = bool(torch.equal(out, ref[0]))
                 n = int(np.count_nonzero(ref[2]))
                 e_bn = float(np.max(np.abs(bn[:n].astype(np.float64) - ref[1][:n]) / ref[1][:n])) if n else 0.0
                 e_dl = float(np.max(np.abs(dl[:n].astype(np.float64) - ref[2][:n]) / ref[2][:n])) if n else 0.0
                 ok = same and e_bn < 1e-6 and e_dl < 1e-6 and int(np.count_nonzero(dl)) == n
                 ok_all &= ok
-                print(json.dumps({"world": world, "grid": list(plan.grid), "schedule": sched, "iterations": iters,
+                print(json.dumps({"world": world, "grid": list(plan.grid), "periodic": periodic, "schedule": sched,
+                                  "iterations": iters,
                                   "stopping": stop, "iterations_run": n, "recon_bit_identical": same,
                                   "bnorm_max_rel": e_bn, "delta_max_rel": e_dl, "ok": ok}), flush=True)
             dist.barrier()
