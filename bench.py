@@ -194,7 +194,7 @@ def workload_config(n):
     g = (SHARD_PER_GPU[0] * n,) + SHARD_PER_GPU[1:]
     return {"workload": f"denoise4D anisotropic FISTA fp32 {'x'.join(map(str, g))} sharded on scan axis 0 over {n} GPUs "
                         f"(BASELINE config 5 shape, {'x'.join(map(str, SHARD_PER_GPU))} per GPU; N=8 is config 5)",
-            "shape": list(g), "shard": list(SHARD_PER_GPU), "halo": "1 plane of b0 right / recon left per half-step (NCCL)",
+            "shape": list(g), "shard": list(SHARD_PER_GPU), "halo": "fused: 1 plane of the new recon left and right per iteration; two_pass: 1 plane of b0 right / recon left per half-step (NCCL send/recv, inline after the halo planes)",
             "l2": "working set 86 GB per GPU >> 126 MB L2"}
 
 

@@ -24,7 +24,10 @@ tile of a split axis exchange planes too and the kernels treat that axis as Jia-
 (``cytvdn_step_opts.flags`` bits 8..11), so the wrap is done by the exchange.
 
 Default layout on NVSwitch: 1-D over axis 0 (contiguous halo planes, two neighbours); the halo planes
-are computed first and travel on a side stream while the interior is computed.  The reference's 2-D
+are computed first, exchanged right away on the compute stream (a 67 MB plane takes ~0.3 ms of a ~28 ms
+iteration and the neighbours' halo planes are ready at the same moment), then the interior is swept.
+Running the exchange on a side stream under the interior sweep (``CYTVDN_SHARD_EXCHANGE=overlap``) was
+measured slower on B200: NCCL's send/recv CTAs displace CTAs of the persistent sweep.  The reference's 2-D
 ``(wx, wy)`` heuristic (`mpi.py:131-150`) is available as ``grid="mpi"`` (no overlap of compute and
 exchange in that mode).
 """
@@ -32,6 +35,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -401,11 +405,16 @@ class CudaShard:
         return self.torch.stack([s[:, 0:4].sum(1), s[:, 4:16:2].sum(1), s[:, 5:16:2].sum(1)], dim=1)
 
 
-def _run_iteration_overlapped(sh: CudaShard, it, tkr, fista, group, comm_stream):
-    """1-D (axis-0) schedule: halo planes first, exchange on ``comm_stream`` under the interior sweep."""
+def _run_iteration_overlapped(sh: CudaShard, it, tkr, fista, group, comm_stream, mode=None):
+    """Two-pass schedule, 1-D (axis-0) split: per half-step the halo planes first, then the exchange -- inline on
+    the compute stream (default) or on ``comm_stream`` under the interior sweep (``mode="overlap"``, see
+    ``_run_iteration_fused``) -- then the rest of the sweep."""
     torch = sh.torch
     main = torch.cuda.current_stream(sh.orig.device)
     plan = sh.plan
+    if mode is None:
+        mode = os.environ.get("CYTVDN_SHARD_EXCHANGE", "inline")
+    overlap = mode == "overlap" and comm_stream is not None
     for phase in ("a", "b"):
         first, rest = plan.a_boxes() if phase == "a" else plan.b_boxes()
         ops = plan.after_a() if phase == "a" else plan.after_b()
@@ -414,30 +423,47 @@ def _run_iteration_overlapped(sh: CudaShard, it, tkr, fista, group, comm_stream)
         for box in first:
             (sh.half_step_a(it, slot, tkr, fista, box) if phase == "a" else sh.half_step_b(it, slot, box))
             slot += step
+
+        def exchange():
+            works, unpack = halo_exchange(ops, sh.arrays, group)
+            for w_ in works:
+                w_.wait()
+            unpack()
+
         if ops:
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev)
-                works, unpack = halo_exchange(ops, sh.arrays, group)
-                for w_ in works:
-                    w_.wait()
-                unpack()
-        for box in rest:          # co-runs with the exchange: dynamic tile scheduling
-            (sh.half_step_a(it, slot, tkr, fista, box, bool(ops)) if phase == "a"
-             else sh.half_step_b(it, slot, box, bool(ops)))
+            if overlap:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev)
+                    exchange()
+            else:
+                exchange()
+        for box in rest:          # in overlap mode it co-runs with the exchange: dynamic tile scheduling
+            dyn = overlap and bool(ops)
+            (sh.half_step_a(it, slot, tkr, fista, box, dyn) if phase == "a" else sh.half_step_b(it, slot, box, dyn))
             slot += step
-        if ops:
+        if ops and overlap:
             main.wait_stream(comm_stream)
 
 
-def _run_iteration_fused(sh: CudaShard, it, tkr, fista, group, comm_stream):
-    """Fused schedule, 1-D split: planes to send first, one exchange of the NEW reconstruction (both
-    directions) on ``comm_stream`` under the interior sweep, then the state sets swap roles."""
+def _run_iteration_fused(sh: CudaShard, it, tkr, fista, group, comm_stream, mode=None):
+    """Fused schedule: planes to send first, then ONE exchange of the NEW reconstruction (both directions),
+    then the state sets swap roles.  Where the exchange runs (1-D split):
+
+    ``mode="inline"`` (default): on the compute stream, right after the halo planes -- it waits only for the
+        neighbours' halo planes (computed at the same moment), costs ~0.3 ms of a ~28 ms iteration and leaves the
+        interior sweep alone on the GPU.
+    ``mode="overlap"``: on ``comm_stream`` under the interior sweep.  Measured SLOWER on B200 (28.4 vs 27.6 ms):
+        NCCL's send/recv CTAs take SMs from the persistent sweep for longer than the transfer itself lasts.
+    """
     torch = sh.torch
     main = torch.cuda.current_stream(sh.orig.device)
     plan = sh.plan
     one_d = plan.grid[1] == 1
+    if mode is None:
+        mode = os.environ.get("CYTVDN_SHARD_EXCHANGE", "inline")
+    overlap = mode == "overlap" and one_d and comm_stream is not None
     first, rest = plan.fused_boxes() if one_d else ([], [(0, plan.local_shape[0])])
     ops = plan.after_fused()
     slot = 0
@@ -445,26 +471,30 @@ def _run_iteration_fused(sh: CudaShard, it, tkr, fista, group, comm_stream):
         sh.fused_step(it, slot, tkr, fista, box)
         slot += 4
     new_arrays = {"recon": sh.recon2}
-    if ops and one_d and comm_stream is not None:
-        ev = torch.cuda.Event()
-        ev.record(main)
-        with torch.cuda.stream(comm_stream):
-            comm_stream.wait_event(ev)
-            works, unpack = halo_exchange(ops, new_arrays, group)
-            for w_ in works:
-                w_.wait()
-            unpack()
-    for box in rest:              # co-runs with the exchange: dynamic tile scheduling
-        sh.fused_step(it, slot, tkr, fista, box, bool(ops) and one_d and comm_stream is not None)
+
+    def exchange():
+        works, unpack = halo_exchange(ops, new_arrays, group)
+        for w_ in works:
+            w_.wait()
+        unpack()
+
+    if ops and one_d:
+        if overlap:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev)
+                exchange()
+        else:
+            exchange()
+    for box in rest:              # in overlap mode it co-runs with the exchange: dynamic tile scheduling
+        sh.fused_step(it, slot, tkr, fista, box, overlap and bool(ops))
         slot += 4
     if ops:
-        if one_d and comm_stream is not None:
+        if overlap:
             main.wait_stream(comm_stream)
-        else:
-            works, unpack = halo_exchange(ops, new_arrays, group)
-            for w_ in works:
-                w_.wait()
-            unpack()
+        elif not one_d:
+            exchange()            # 2-D grids: the strided halo planes are exchanged after the full sweep
     sh.fused_swap()
 
 
