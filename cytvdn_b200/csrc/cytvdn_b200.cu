@@ -5,6 +5,7 @@
 #include "../../include/cytvdn_b200.h"
 #include "kernels.cuh"
 #include "fused.cuh"
+#include "fused_tma.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -98,7 +99,7 @@ int dev_info(DevInfo *d)
 }
 
 template <typename K>
-int grid_for(K kernel, int ntiles, int *grid)
+int grid_for(K kernel, int ntiles, int *grid, size_t dyn_smem = 0)
 {
     static std::mutex m;
     static std::map<std::pair<int, const void *>, int> cache;
@@ -112,7 +113,9 @@ int grid_for(K kernel, int ntiles, int *grid)
         auto key = std::make_pair(dev, (const void *)kernel);
         auto it = cache.find(key);
         if (it == cache.end()) {
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
+            if (dyn_smem > 0)
+                CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn_smem));
             if (per_sm < 1) per_sm = 1;
             static const char *env = getenv("CYTVDN_CTAS_PER_SM");
             if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
@@ -429,13 +432,32 @@ int run_fused(const FusedCall &c)
         return CYTVDN_OK;
     }
     int grid = 1;
+    const bool ax2 = c.D.ndim == 4;
+    // experimental TMA-staged variant (measured slower, see fused_tma.cuh): opt-in, vector path, static tile order
+    bool use_tma = false;
+    { const char *env = getenv("CYTVDN_FUSED_TMA"); if (env && !strcmp(env, "1")) use_tma = vec && !P.S.dynamic; }
+    if (use_tma) {
+        const int nself = 2 + ((ax2 ? 3 : 2) + 1) * (c.fista ? 2 : 1);
+        const size_t smem = (size_t)2 * nself * kBlock * 16;
+#define LAUNCH_TMA(FV, AX2V)                                                           \
+    do {                                                                               \
+        auto k = tv_fused_tma_kernel<T, vec_width<T>(), FV, AX2V>;                     \
+        if (int rc = grid_for(k, P.S.ntiles, &grid, smem)) return rc;                  \
+        k<<<grid, kBlock, smem, c.st>>>(P);                                            \
+    } while (0)
+        if (c.fista) { if (ax2) LAUNCH_TMA(true, true); else LAUNCH_TMA(true, false); }
+        else         { if (ax2) LAUNCH_TMA(false, true); else LAUNCH_TMA(false, false); }
+#undef LAUNCH_TMA
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+        return CYTVDN_OK;
+    }
 #define LAUNCH_FUSED(VWV, FV, AX2V)                                                    \
     do {                                                                               \
         auto k = tv_fused_kernel<T, VWV, FV, AX2V>;                                    \
         if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;                        \
         k<<<grid, kBlock, 0, c.st>>>(P);                                               \
     } while (0)
-    const bool ax2 = c.D.ndim == 4;
     if (vec) {
         if (c.fista) { if (ax2) LAUNCH_FUSED(vec_width<T>(), true, true); else LAUNCH_FUSED(vec_width<T>(), true, false); }
         else         { if (ax2) LAUNCH_FUSED(vec_width<T>(), false, true); else LAUNCH_FUSED(vec_width<T>(), false, false); }

@@ -111,3 +111,59 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt, f
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """Bad arguments are rejected with CYTVDN_E_INVALID / _UNSUPPORTED and a message before any CUDA call."""
+    from cytvdn_b200 import _lib
+    lib = _lib.load()
+    sh4 = (C.c_int64 * 4)(4, 4, 4, 4)
+    one = C.c_void_p(16)            # never dereferenced: validation fails first
+    err = lambda: lib.cytvdn_last_error().decode()
+    assert lib.cytvdn_accumulator_update(5, sh4, 0, one, one, None, 0.0, 0, 1.0, 2, one, None, None) == 1
+    assert "ndim must be 3 or 4" in err()
+    assert lib.cytvdn_accumulator_update(4, sh4, 7, one, one, None, 0.0, 0, 1.0, 2, one, None, None) == 1
+    assert "dtype" in err()
+    assert lib.cytvdn_accumulator_update(4, sh4, 0, None, one, None, 0.0, 0, 1.0, 2, one, None, None) == 1
+    assert "NULL" in err()
+    assert lib.cytvdn_accumulator_update(4, sh4, 0, one, one, None, 0.0, 4, 1.0, 2, one, None, None) == 1
+    assert "ax=4" in err()
+    assert lib.cytvdn_accumulator_update(3, sh4, 0, one, one, None, 0.0, 3, 1.0, 2, one, None, None) == 1
+    assert lib.cytvdn_accumulator_update(4, sh4, 0, one, one, None, 0.0, 0, 1.0, 3, one, None, None) == 1
+    assert "BC_mode" in err()
+    bad = (C.c_int64 * 4)(4, 0, 4, 4)
+    assert lib.cytvdn_accumulator_update(4, bad, 0, one, one, None, 0.0, 0, 1.0, 2, one, None, None) == 1
+    assert "shape[1]" in err()
+    m1 = (C.c_int64 * 4)(1, 4, 4, 4)
+    assert lib.cytvdn_accumulator_update(4, m1, 0, one, one, None, 0.0, 0, 1.0, 1, one, None, None) == 1
+    assert "mirror" in err()
+    assert lib.cytvdn_iso_accumulator_update(sh4, 0, one, one, one, None, None, 0.0, 1, 1, 1.0, one, None, None) == 1
+    assert "different axes" in err()
+    assert lib.cytvdn_iso_accumulator_update(sh4, 0, one, one, one, one, None, 0.0, 0, 1, 1.0, one, None, None) == 1
+    bp = (C.c_void_p * 4)(16, 16, 16, 16)
+    w = (C.c_double * 4)(.1, .1, .1, .1)
+    assert lib.cytvdn_datacube_update(4, sh4, 0, one, one, one, bp, w, 1, one, None, None) == 4     # mirror: unsupported
+    assert "undefined behaviour" in err()
+    assert lib.cytvdn_fused_iteration(4, sh4, 0, one, one, one, bp, bp, None, bp, 0.0, w, w, 2, one, None, None) == 1
+    assert "d_in and d_out" in err()
+    assert lib.cytvdn_fused_iteration(4, sh4, 0, one, one, one, bp, bp, None, None, 0.0, w, w, 1, one, None, None) == 4
+    P = _lib.DenoiseParams()
+    P.ndim, P.dtype = 4, 0
+    for k in range(4):
+        P.shape[k] = 4
+    P.iters_fista = -1
+    assert lib.cytvdn_denoise(C.byref(P), one, one, None, None, None, None, None, None) == 1
+    assert "negative iteration count" in err()
+    P.iters_fista, P.bc_mode = 2, 1
+    assert lib.cytvdn_denoise(C.byref(P), one, one, None, None, None, None, None, None) == 4
+    P.bc_mode, P.ndim, P.isotropic_R = 2, 3, 1
+    assert lib.cytvdn_denoise(C.byref(P), one, one, None, None, None, None, None, None) == 1
+    assert "4-D only" in err()
+    n = C.c_int64(0)
+    P.ndim, P.isotropic_R, P.iters_fista, P.iters_plain = 4, 0, 10, 0
+    assert lib.cytvdn_denoise_workspace_bytes(C.byref(P), 1, 1, C.byref(n)) == 0
+    assert n.value == (8 * 2 + 1) * 4 * 256            # fused: two b/d sets + the second recon buffer
+    P.schedule = 1
+    assert lib.cytvdn_denoise_workspace_bytes(C.byref(P), 0, 0, C.byref(n)) == 0
+    assert n.value == (8 + 2) * 4 * 256                # two-pass from host data: b, d, orig, recon
+    assert lib.cytvdn_launch_count() >= 0
