@@ -96,6 +96,7 @@ __device__ __forceinline__ Coord locate(const Sweep &S, int32_t t)
 // ---- vectors of VW elements (16 bytes when VW > 1) -------------------------------------------
 template <typename T, int VW> struct Raw;
 template <> struct Raw<float, 4>  { typedef float4  type; };
+template <> struct Raw<float, 2>  { typedef float2  type; };
 template <> struct Raw<float, 1>  { typedef float   type; };
 template <> struct Raw<double, 2> { typedef double2 type; };
 template <> struct Raw<double, 1> { typedef double  type; };
@@ -163,6 +164,12 @@ __device__ __forceinline__ float4 ldg_nc_hint(const float4 *p, uint64_t pol)
         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
     return r;
 }
+__device__ __forceinline__ float2 ldg_nc_hint(const float2 *p, uint64_t pol)
+{
+    float2 r;
+    asm("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ double2 ldg_nc_hint(const double2 *p, uint64_t pol)
 {
     double2 r;
@@ -193,6 +200,12 @@ __device__ __forceinline__ float4 ldg_nc_stream(const float4 *p, uint64_t pol)
     float4 r;
     asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_nc_stream(const float2 *p, uint64_t pol)
+{
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ double2 ldg_nc_stream(const double2 *p, uint64_t pol)
@@ -229,6 +242,12 @@ __device__ __forceinline__ float4 ldg_nc_ordered(const float4 *p)
 {
     float4 r;
     asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float2 ldg_nc_ordered(const float2 *p)
+{
+    float2 r;
+    asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ double2 ldg_nc_ordered(const double2 *p)

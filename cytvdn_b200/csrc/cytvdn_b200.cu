@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -223,9 +224,31 @@ int make_sweep(const Dims &D, int vw, size_t elem, const cytvdn_step_opts *o, in
     return CYTVDN_OK;
 }
 
-bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
 template <typename T> constexpr int vec_width() { return 16 / (int)sizeof(T); }
+
+// Elements per thread: 16-byte vectors when every row start is 16-byte aligned (extent of the fast axis a
+// multiple of the vector width and all base pointers aligned); 8-byte vectors for float rows of even length;
+// else scalar.  `ptr_bits` = OR of all base pointers of the launch.
+template <typename T>
+int pick_vw(int64_t n3, uintptr_t ptr_bits)
+{
+    constexpr int full = vec_width<T>();
+    if (n3 % full == 0 && (ptr_bits & 15u) == 0) return full;
+    if (sizeof(T) == 4 && n3 % 2 == 0 && (ptr_bits & 7u) == 0) return 2;
+    return 1;
+}
+inline uintptr_t bits(const void *p) { return reinterpret_cast<uintptr_t>(p); }
+
+// call f(std::integral_constant<int, VW>) for the run-time vector width
+template <typename T, typename F>
+int dispatch_vw(int vw, F &&f)
+{
+    if (vw == vec_width<T>()) return f(std::integral_constant<int, vec_width<T>()>{});
+    if constexpr (sizeof(T) == 4) {
+        if (vw == 2) return f(std::integral_constant<int, 2>{});
+    }
+    return f(std::integral_constant<int, 1>{});
+}
 
 // ---- half-step A -------------------------------------------------------------------------------
 template <typename T, int VW, bool FISTA>
@@ -280,7 +303,7 @@ int run_acc(const AccCall &c)
 {
     AccParams<T> P;
     memset(&P, 0, sizeof P);
-    bool vec = (c.D.n[3] % vec_width<T>() == 0) && aligned16(c.a);
+    uintptr_t pb = bits(c.a);
     int nax = 0;
     for (int k = 0; k < 4; ++k) {
         const bool on = c.mode == ACC_ALL4 ? true : c.mode == ACC_ALL3 ? (k != 2) : ((c.axmask >> k) & 1);
@@ -290,11 +313,11 @@ int run_acc(const AccCall &c)
         ++nax;
         if (!c.b[k]) return fail(CYTVDN_E_INVALID, "accumulator for axis slot %d is NULL", k);
         if (c.fista && !c.d[k]) return fail(CYTVDN_E_INVALID, "FISTA auxiliary for axis slot %d is NULL", k);
-        vec = vec && aligned16(c.b[k]) && (!c.fista || aligned16(c.d[k]));
+        pb |= bits(c.b[k]) | (c.fista ? bits(c.d[k]) : 0);
         P.b[k] = (T *)c.b[k];
         P.d[k] = (T *)c.d[k];
     }
-    const int vw = vec ? vec_width<T>() : 1;
+    const int vw = pick_vw<T>(c.D.n[3], pb);
     if (int rc = make_sweep(c.D, vw, sizeof(T), c.opts, 1 + nax * (c.fista ? 2 : 1), &P.S)) return rc;
     P.u = (const T *)c.a;
     P.tk = (T)c.tk;
@@ -307,11 +330,10 @@ int run_acc(const AccCall &c)
         CUDA_TRY(cudaMemsetAsync(c.norm_dev, 0, sizeof(double), c.st));
         return CYTVDN_OK;
     }
-    if (vec) {
-        return c.fista ? launch_acc_mode<T, vec_width<T>(), true>(c.mode, P, c.st)
-                       : launch_acc_mode<T, vec_width<T>(), false>(c.mode, P, c.st);
-    }
-    return c.fista ? launch_acc_mode<T, 1, true>(c.mode, P, c.st) : launch_acc_mode<T, 1, false>(c.mode, P, c.st);
+    return dispatch_vw<T>(vw, [&](auto VWc) {
+        constexpr int VW = decltype(VWc)::value;
+        return c.fista ? launch_acc_mode<T, VW, true>(c.mode, P, c.st) : launch_acc_mode<T, VW, false>(c.mode, P, c.st);
+    });
 }
 
 int check_common(int dtype, const void *a, const double *out_dev)
@@ -329,16 +351,16 @@ int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const 
 {
     DcuParams<T> P;
     memset(&P, 0, sizeof P);
-    bool vec = (D.n[3] % vec_width<T>() == 0) && aligned16(orig) && aligned16(uin) && aligned16(uout);
+    uintptr_t pb = bits(orig) | bits(uin) | bits(uout);
     for (int k = 0; k < D.ndim; ++k) {
         const int s = D.axmap[k];
         if (!b[k]) return fail(CYTVDN_E_INVALID, "b[%d] is NULL", k);
-        vec = vec && aligned16(b[k]);
+        pb |= bits(b[k]);
         P.b[s] = (const T *)b[k];
         P.w[s] = (T)w[k];
         if ((zero_wrap >> k) & 1) P.zero_wrap |= 1 << s;
     }
-    const int vw = vec ? vec_width<T>() : 1;
+    const int vw = pick_vw<T>(D.n[3], pb);
     if (int rc = make_sweep(D, vw, sizeof(T), opts, 2 + D.ndim, &P.S)) return rc;
     P.f = (const T *)orig; P.uin = (const T *)uin; P.uout = (T *)uout;
     Workspace ws;
@@ -348,16 +370,21 @@ int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const 
         CUDA_TRY(cudaMemsetAsync(sums_dev, 0, 2 * sizeof(double), st));
         return CYTVDN_OK;
     }
-    int grid = 1;
-#define LAUNCH_DCU(VWV, AX2V)                                                          \
-    do {                                                                               \
-        auto k = tv_datacube_kernel<T, VWV, AX2V>;                                     \
-        if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;                        \
-        k<<<grid, kBlock, 0, st>>>(P);                                                 \
-    } while (0)
-    if (vec) { if (D.ndim == 4) LAUNCH_DCU(vec_width<T>(), true); else LAUNCH_DCU(vec_width<T>(), false); }
-    else     { if (D.ndim == 4) LAUNCH_DCU(1, true); else LAUNCH_DCU(1, false); }
-#undef LAUNCH_DCU
+    if (int rc = dispatch_vw<T>(vw, [&](auto VWc) -> int {
+            constexpr int VW = decltype(VWc)::value;
+            int grid = 1;
+            if (D.ndim == 4) {
+                auto k = tv_datacube_kernel<T, VW, true>;
+                if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
+                k<<<grid, kBlock, 0, st>>>(P);
+            } else {
+                auto k = tv_datacube_kernel<T, VW, false>;
+                if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
+                k<<<grid, kBlock, 0, st>>>(P);
+            }
+            return CYTVDN_OK;
+        }))
+        return rc;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return CYTVDN_OK;
@@ -402,7 +429,7 @@ int run_fused(const FusedCall &c)
 {
     FusedParams<T> P;
     memset(&P, 0, sizeof P);
-    bool vec = (c.D.n[3] % vec_width<T>() == 0) && aligned16(c.orig) && aligned16(c.uin) && aligned16(c.uout);
+    uintptr_t pb = bits(c.orig) | bits(c.uin) | bits(c.uout);
     int nax = 0;
     for (int k = 0; k < 4; ++k) {
         if (c.D.ndim == 3 && k == 2) continue;
@@ -411,14 +438,14 @@ int run_fused(const FusedCall &c)
         if (c.fista && (!c.din[k] || !c.dout[k])) return fail(CYTVDN_E_INVALID, "FISTA auxiliary in/out for axis slot %d is NULL", k);
         if (c.bin[k] == c.bout[k] || (c.fista && c.din[k] == c.dout[k]))
             return fail(CYTVDN_E_INVALID, "the fused iteration is out of place: in and out arrays must differ");
-        vec = vec && aligned16(c.bin[k]) && aligned16(c.bout[k]) &&
-              (!c.fista || (aligned16(c.din[k]) && aligned16(c.dout[k])));
+        pb |= bits(c.bin[k]) | bits(c.bout[k]) | (c.fista ? (bits(c.din[k]) | bits(c.dout[k])) : 0);
         P.bin[k] = (const T *)c.bin[k]; P.bout[k] = (T *)c.bout[k];
         P.din[k] = (const T *)c.din[k]; P.dout[k] = (T *)c.dout[k];
         P.clip[k] = (T)c.clip[k]; P.w[k] = (T)c.w[k]; P.bc[k] = c.bc[k];
     }
     if (c.uin == c.uout) return fail(CYTVDN_E_INVALID, "the fused iteration is out of place: recon_in == recon_out");
-    const int vw = vec ? vec_width<T>() : 1;
+    const int vw = pick_vw<T>(c.D.n[3], pb);
+    const bool vec = vw == vec_width<T>();
     // every array of the sweep transits L2 and recon must survive 2*TJ planes (read as x+e0, x, x-e0)
     const int arrays = 3 + nax * (c.fista ? 4 : 2);
     if (int rc = make_sweep(c.D, vw, sizeof(T), c.opts, 2 * arrays, &P.S)) return rc;
@@ -452,20 +479,17 @@ int run_fused(const FusedCall &c)
         CUDA_TRY(cudaGetLastError());
         return CYTVDN_OK;
     }
-#define LAUNCH_FUSED(VWV, FV, AX2V)                                                    \
-    do {                                                                               \
-        auto k = tv_fused_kernel<T, VWV, FV, AX2V>;                                    \
-        if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;                        \
-        k<<<grid, kBlock, 0, c.st>>>(P);                                               \
-    } while (0)
-    if (vec) {
-        if (c.fista) { if (ax2) LAUNCH_FUSED(vec_width<T>(), true, true); else LAUNCH_FUSED(vec_width<T>(), true, false); }
-        else         { if (ax2) LAUNCH_FUSED(vec_width<T>(), false, true); else LAUNCH_FUSED(vec_width<T>(), false, false); }
-    } else {
-        if (c.fista) { if (ax2) LAUNCH_FUSED(1, true, true); else LAUNCH_FUSED(1, true, false); }
-        else         { if (ax2) LAUNCH_FUSED(1, false, true); else LAUNCH_FUSED(1, false, false); }
-    }
-#undef LAUNCH_FUSED
+    if (int rc = dispatch_vw<T>(vw, [&](auto VWc) -> int {
+            constexpr int VW = decltype(VWc)::value;
+            auto go = [&](auto k) -> int {
+                if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
+                k<<<grid, kBlock, 0, c.st>>>(P);
+                return CYTVDN_OK;
+            };
+            if (c.fista) return ax2 ? go(tv_fused_kernel<T, VW, true, true>) : go(tv_fused_kernel<T, VW, true, false>);
+            return ax2 ? go(tv_fused_kernel<T, VW, false, true>) : go(tv_fused_kernel<T, VW, false, false>);
+        }))
+        return rc;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return CYTVDN_OK;

@@ -165,6 +165,9 @@ CASES_4D = [
     ((9, 13, 16, 32), "float32", dict(iterations=25, FISTA=True), None),
     ((9, 13, 16, 32), "float32", dict(iterations=25, FISTA=True), 0.05),
     ((7, 10, 9, 11), "float32", dict(iterations=20, FISTA=True), 0.01),      # odd extents: scalar path
+    ((7, 10, 9, 10), "float32", dict(iterations=20, FISTA=True), 0.01),      # even, not % 4: 8-byte vectors
+    ((5, 6, 7, 134), "float32", dict(iterations=12, FISTA=False), None),     # 8-byte vectors, rows longer than a warp
+    ((5, 6, 7, 134), "float32", dict(iterations=12, FISTA=True, BC_mode=0), 0.02),
     ((6, 7, 5, 6), "float64", dict(iterations=30, FISTA=True), 0.002),
     ((12, 9, 8, 16), "float64", dict(iterations=20, FISTA=False), None),
     ((8, 8, 16, 16), "float32", dict(iterations=[10, 10]), 0.03),
@@ -199,6 +202,8 @@ CASES_3D = [
     ((9, 11, 64), "float32", dict(iterations=30, FISTA=False), None),
     ((9, 11, 64), "float32", dict(iterations=30, FISTA=True), 0.004),
     ((7, 5, 37), "float32", dict(iterations=20, FISTA=True), 0.001),
+    ((7, 5, 38), "float32", dict(iterations=20, FISTA=True), 0.001),        # 8-byte vectors
+    ((6, 5, 1998), "float32", dict(iterations=10, FISTA=False, BC_mode=0), None),
     ((6, 9, 50), "float64", dict(iterations=25, FISTA=True, BC_mode=0), 0.002),
     ((5, 1, 16), "float32", dict(iterations=8, FISTA=True), None),
     ((1, 1, 1), "float64", dict(iterations=3, FISTA=False), None),
