@@ -30,6 +30,7 @@ class StepOpts(C.Structure):
         ("zero_wrap_mask", C.c_int32),
         ("flags", C.c_int32),
         ("l2_budget_bytes", C.c_int64),
+        ("row_pitch", C.c_int64),
     ]
 
 

@@ -41,7 +41,8 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f)
 struct Sweep {
     int64_t st0, st1;          // element strides of axes 0 and 1
     int32_t n0, n1, n2, n3;    // extents
-    int32_t n3v, mv;           // vectors per row / per inner plane (n2*n3v)
+    int32_t n3p;               // row pitch in elements (>= n3; > n3 for rows padded to the vector width)
+    int32_t n3v, mv;           // vectors per (padded) row / per inner plane (n2*n3v)
     int32_t i0, j0, ni;        // sweep box: axis-0 origin/extent, axis-1 origin
     int32_t tj, tl, nfull;     // strip width, width of the trailing partial strip (0: none), #full strips
     int32_t cps_full, cps_last;// chunks per (i, strip) slab
@@ -55,6 +56,8 @@ struct Sweep {
 struct Coord {                 // what one thread works on
     int64_t e;                 // element offset of the first of its VW voxels
     int32_t i, j, k, l0;
+    int32_t vl;                // index of the last real voxel in this vector (VW-1 unless the row ends inside it)
+    bool row_end;              // this vector holds the last real voxel of its row
     bool active, owned;
 };
 
@@ -87,6 +90,8 @@ __device__ __forceinline__ Coord locate(const Sweep &S, int32_t t)
     const int32_t m = qq - jj * S.mv;
     p.k = (int32_t)fdiv((uint32_t)m, S.d_n3v);
     p.l0 = (m - p.k * S.n3v) * VW;
+    p.row_end = p.l0 + VW >= S.n3;
+    p.vl = p.row_end ? S.n3 - 1 - p.l0 : VW - 1;
     p.j = jb + jj;
     p.e = (int64_t)p.i * S.st0 + (int64_t)jb * S.st1 + (int64_t)qq * VW;
     p.owned = p.active && p.i >= S.oi0 && p.i < S.oi1 && p.j >= S.oj0 && p.j < S.oj1;

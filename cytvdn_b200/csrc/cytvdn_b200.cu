@@ -138,9 +138,10 @@ struct Dims {
     int ndim;
     int64_t n[4];     // embedded 4-D extents ([N0,N1,1,N2] for 3-D)
     int axmap[4];     // user axis -> embedded axis
+    int64_t pitch;    // elements between rows of the fast axis (>= n[3])
 };
 
-int make_dims(int ndim, const int64_t *shape, Dims *D)
+int make_dims(int ndim, const int64_t *shape, Dims *D, const cytvdn_step_opts *opts = nullptr)
 {
     if (ndim != 3 && ndim != 4) return fail(CYTVDN_E_INVALID, "ndim must be 3 or 4 (got %d)", ndim);
     if (!shape) return fail(CYTVDN_E_INVALID, "shape is NULL");
@@ -153,6 +154,13 @@ int make_dims(int ndim, const int64_t *shape, Dims *D)
     } else {
         D->n[0] = shape[0]; D->n[1] = shape[1]; D->n[2] = 1; D->n[3] = shape[2];
         D->axmap[0] = 0; D->axmap[1] = 1; D->axmap[2] = 3; D->axmap[3] = -1;
+    }
+    D->pitch = D->n[3];
+    if (opts && opts->row_pitch > 0) {
+        if (opts->row_pitch < D->n[3] || opts->row_pitch > 0x7fffffff)
+            return fail(CYTVDN_E_INVALID, "row_pitch %lld is smaller than the row length %lld", (long long)opts->row_pitch,
+                        (long long)D->n[3]);
+        D->pitch = opts->row_pitch;
     }
     return CYTVDN_OK;
 }
@@ -171,10 +179,12 @@ int make_sweep(const Dims &D, int vw, size_t elem, const cytvdn_step_opts *o, in
 {
     memset(S, 0, sizeof *S);
     S->n0 = (int32_t)D.n[0]; S->n1 = (int32_t)D.n[1]; S->n2 = (int32_t)D.n[2]; S->n3 = (int32_t)D.n[3];
-    S->st1 = D.n[2] * D.n[3];
+    S->n3p = (int32_t)D.pitch;
+    if (D.pitch % vw) return fail(CYTVDN_E_INVALID, "internal: row pitch %lld not a multiple of the vector width %d", (long long)D.pitch, vw);
+    S->st1 = D.n[2] * D.pitch;
     S->st0 = D.n[1] * S->st1;
     if (S->st1 / vw > 0x3fffffff) return fail(CYTVDN_E_INVALID, "inner plane too large");
-    S->n3v = (int32_t)(D.n[3] / vw);
+    S->n3v = (int32_t)(D.pitch / vw);
     S->mv = (int32_t)(S->st1 / vw);
     int64_t lo[2] = {0, 0}, hi[2] = {D.n[0], D.n[1]}, olo[2] = {0, 0}, ohi[2] = {D.n[0], D.n[1]};
     if (o) {
@@ -317,7 +327,7 @@ int run_acc(const AccCall &c)
         P.b[k] = (T *)c.b[k];
         P.d[k] = (T *)c.d[k];
     }
-    const int vw = pick_vw<T>(c.D.n[3], pb);
+    const int vw = pick_vw<T>(c.D.pitch, pb);
     if (int rc = make_sweep(c.D, vw, sizeof(T), c.opts, 1 + nax * (c.fista ? 2 : 1), &P.S)) return rc;
     P.u = (const T *)c.a;
     P.tk = (T)c.tk;
@@ -360,7 +370,7 @@ int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const 
         P.w[s] = (T)w[k];
         if ((zero_wrap >> k) & 1) P.zero_wrap |= 1 << s;
     }
-    const int vw = pick_vw<T>(D.n[3], pb);
+    const int vw = pick_vw<T>(D.pitch, pb);
     if (int rc = make_sweep(D, vw, sizeof(T), opts, 2 + D.ndim, &P.S)) return rc;
     P.f = (const T *)orig; P.uin = (const T *)uin; P.uout = (T *)uout;
     Workspace ws;
@@ -391,7 +401,7 @@ int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const 
 }
 
 template <typename T>
-int run_sse(int64_t n, const void *a, const void *b, double *out, cudaStream_t st)
+int run_sse(int64_t n, const void *a, const void *b, double *out, cudaStream_t st, int64_t n3 = 1, int64_t n3p = 1)
 {
     Workspace ws;
     if (int rc = get_workspace(st, &ws)) return rc;
@@ -401,7 +411,7 @@ int run_sse(int64_t n, const void *a, const void *b, double *out, cudaStream_t s
     auto k = tv_sse_kernel<T>;
     const int64_t blocks = (n + kBlock - 1) / kBlock;
     if (int rc = grid_for(k, (int)(blocks > 0x7fffffff ? 0x7fffffff : blocks), &grid)) return rc;
-    k<<<grid, kBlock, 0, st>>>((const T *)a, (const T *)b, n, W);
+    k<<<grid, kBlock, 0, st>>>((const T *)a, (const T *)b, n, (int32_t)n3, (int32_t)n3p, W);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return CYTVDN_OK;
@@ -444,7 +454,7 @@ int run_fused(const FusedCall &c)
         P.clip[k] = (T)c.clip[k]; P.w[k] = (T)c.w[k]; P.bc[k] = c.bc[k];
     }
     if (c.uin == c.uout) return fail(CYTVDN_E_INVALID, "the fused iteration is out of place: recon_in == recon_out");
-    const int vw = pick_vw<T>(c.D.n[3], pb);
+    const int vw = pick_vw<T>(c.D.pitch, pb);
     const bool vec = vw == vec_width<T>();
     // every array of the sweep transits L2 and recon must survive 2*TJ planes (read as x+e0, x, x-e0)
     const int arrays = 3 + nax * (c.fista ? 4 : 2);
@@ -462,7 +472,7 @@ int run_fused(const FusedCall &c)
     const bool ax2 = c.D.ndim == 4;
     // experimental TMA-staged variant (measured slower, see fused_tma.cuh): opt-in, vector path, static tile order
     bool use_tma = false;
-    { const char *env = getenv("CYTVDN_FUSED_TMA"); if (env && !strcmp(env, "1")) use_tma = vec && !P.S.dynamic; }
+    { const char *env = getenv("CYTVDN_FUSED_TMA"); if (env && !strcmp(env, "1")) use_tma = vec && !P.S.dynamic && P.S.n3p == P.S.n3; }
     if (use_tma) {
         const int nself = 2 + ((ax2 ? 3 : 2) + 1) * (c.fista ? 2 : 1);
         const size_t smem = (size_t)2 * nself * kBlock * 16;
@@ -527,7 +537,7 @@ int cytvdn_accumulator_update(int ndim, const int64_t *shape, int dtype, const v
 {
     AccCall c;
     memset(&c, 0, sizeof c);
-    if (int rc = make_dims(ndim, shape, &c.D)) return rc;
+    if (int rc = make_dims(ndim, shape, &c.D, opts)) return rc;
     if (int rc = check_common(dtype, a, norm_dev)) return rc;
     if (ax < 0 || ax >= ndim) return fail(CYTVDN_E_INVALID, "ax=%d out of range for ndim=%d", ax, ndim);
     if (bc_mode < 0 || bc_mode > 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1 or 2");
@@ -546,7 +556,7 @@ int cytvdn_iso_accumulator_update(const int64_t *shape, int dtype, const void *a
 {
     AccCall c;
     memset(&c, 0, sizeof c);
-    if (int rc = make_dims(4, shape, &c.D)) return rc;
+    if (int rc = make_dims(4, shape, &c.D, opts)) return rc;
     if (int rc = check_common(dtype, a, norm_dev)) return rc;
     if (ax1 < 0 || ax1 > 3 || ax2 < 0 || ax2 > 3 || ax1 == ax2)
         return fail(CYTVDN_E_INVALID, "ax1/ax2 must be two different axes in 0..3 (got %d, %d)", ax1, ax2);
@@ -566,7 +576,7 @@ int cytvdn_accumulator_update_all(int ndim, const int64_t *shape, int dtype, con
 {
     AccCall c;
     memset(&c, 0, sizeof c);
-    if (int rc = make_dims(ndim, shape, &c.D)) return rc;
+    if (int rc = make_dims(ndim, shape, &c.D, opts)) return rc;
     if (int rc = check_common(dtype, a, norm_dev)) return rc;
     if (!b || !clip) return fail(CYTVDN_E_INVALID, "b / clip is NULL");
     if (bc_mode < 0 || bc_mode > 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1 or 2");
@@ -592,7 +602,7 @@ int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void
                            double *sums_dev, const cytvdn_step_opts *opts, void *stream)
 {
     Dims D;
-    if (int rc = make_dims(ndim, shape, &D)) return rc;
+    if (int rc = make_dims(ndim, shape, &D, opts)) return rc;
     if (int rc = check_common(dtype, orig, sums_dev)) return rc;
     if (!recon_in || !recon_out || !b || !lambda_mu) return fail(CYTVDN_E_INVALID, "recon / b / lambda_mu is NULL");
     if (bc_mode == 1)
@@ -612,7 +622,7 @@ int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void
 {
     FusedCall c;
     memset(&c, 0, sizeof c);
-    if (int rc = make_dims(ndim, shape, &c.D)) return rc;
+    if (int rc = make_dims(ndim, shape, &c.D, opts)) return rc;
     if (int rc = check_common(dtype, orig, sums_dev)) return rc;
     if (!recon_in || !recon_out || !b_in || !b_out || !clip || !lambda_mu)
         return fail(CYTVDN_E_INVALID, "recon / b / clip / lambda_mu is NULL");
@@ -724,9 +734,11 @@ int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *p, int data_on_d
     Dims D;
     if (int rc = validate_params(p, &D)) return rc;
     if (!bytes) return fail(CYTVDN_E_INVALID, "bytes is NULL");
-    const int64_t nb = D.n[0] * D.n[1] * D.n[2] * D.n[3] * (p->dtype == CYTVDN_F32 ? 4 : 8);
+    const int64_t elem = p->dtype == CYTVDN_F32 ? 4 : 8, vwf = 16 / elem;
+    const bool padded = D.n[3] % vwf != 0;             // internal rows are padded: caller arrays are always copied
+    const int64_t nb = D.n[0] * D.n[1] * D.n[2] * ((D.n[3] + vwf - 1) / vwf * vwf) * elem;
     const bool fused = fused_possible(p) && requested_schedule(p) != 1;
-    *bytes = arrays_needed(p, fused, data_on_device != 0, recon_on_device != 0, false) * nb;
+    *bytes = arrays_needed(p, fused, data_on_device != 0 && !padded, recon_on_device != 0 && !padded, false) * nb;
     return CYTVDN_OK;
 }
 
@@ -771,12 +783,23 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     if (nIt > 0 && (!bnorm || !delta)) return fail(CYTVDN_E_INVALID, "bnorm / delta is NULL");
     if (reference_data && !mse) return fail(CYTVDN_E_INVALID, "mse is NULL but reference_data was given");
     const size_t elem = p->dtype == CYTVDN_F32 ? 4 : 8;
-    const int64_t nvox = D.n[0] * D.n[1] * D.n[2] * D.n[3];
-    const size_t nb = (size_t)nvox * elem;
     const int nd = p->ndim;
+    // Rows whose length is not a multiple of the 16-byte vector width are PADDED in the internal state (pitch
+    // rounded up), so every shape runs on the vector path; the pad voxels are inert (cytvdn_step_opts.row_pitch).
+    // Caller arrays stay dense: they are converted by 2-D copies on the way in and out.
+    const int64_t full_vw = 16 / (int64_t)elem;
+    bool padded = D.n[3] % full_vw != 0;
+    { const char *env = getenv("CYTVDN_PAD_ROWS"); if (env && !strcmp(env, "0")) padded = false; }
+    const int64_t n3 = D.n[3], n3p = padded ? (n3 + full_vw - 1) / full_vw * full_vw : n3;
+    const int64_t rows = D.n[0] * D.n[1] * D.n[2];
+    const int64_t nvox = rows * n3p;                    // voxels of one internal array (pads included)
+    const size_t nb = (size_t)nvox * elem;
+    cytvdn_step_opts sopts;
+    memset(&sopts, 0, sizeof sopts);
+    sopts.row_pitch = n3p;
 
-    const bool data_dev = is_device_ptr(data), recon_dev = is_device_ptr(recon);
-    const bool ref_dev = reference_data ? is_device_ptr(reference_data) : false;
+    const bool data_dev = is_device_ptr(data) && !padded, recon_dev = is_device_ptr(recon) && !padded;
+    const bool ref_dev = reference_data ? (is_device_ptr(reference_data) && !padded) : false;
     int prev_dev = -1;
     CUDA_TRY(cudaGetDevice(&prev_dev));
     if (!data_dev && p->device >= 0) CUDA_TRY(cudaSetDevice(p->device));
@@ -812,14 +835,28 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     void *b[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, *d[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     void *orig_d = nullptr, *rbuf[2] = {nullptr, nullptr}, *ref_d = nullptr;
     double *sums_d = nullptr;
+    // dense caller array -> internal array (any direction the pointers imply; pads zeroed)
+    auto copy_in = [&](void *dst, const void *src) -> int {
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDefault, st)); return CYTVDN_OK; }
+        CUDA_TRY(cudaMemsetAsync(dst, 0, nb, st));
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)n3p * elem, src, (size_t)n3 * elem, (size_t)n3 * elem, (size_t)rows,
+                                   cudaMemcpyDefault, st));
+        return CYTVDN_OK;
+    };
+    auto copy_out = [&](void *dst, const void *src) -> int {
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDefault, st)); return CYTVDN_OK; }
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)n3 * elem, src, (size_t)n3p * elem, (size_t)n3 * elem, (size_t)rows,
+                                   cudaMemcpyDefault, st));
+        return CYTVDN_OK;
+    };
     if (data_dev) orig_d = const_cast<void *>(data);
-    else { if (int rc = pool.alloc(&orig_d, nb)) return rc; CUDA_TRY(cudaMemcpyAsync(orig_d, data, nb, cudaMemcpyHostToDevice, st)); }
+    else { if (int rc = pool.alloc(&orig_d, nb)) return rc; if (int rc = copy_in(orig_d, data)) return rc; }
     if (recon_dev) rbuf[0] = recon;
     else if (int rc = pool.alloc(&rbuf[0], nb)) return rc;
     if (fused) if (int rc = pool.alloc(&rbuf[1], nb)) return rc;
     if (reference_data) {
         if (ref_dev) ref_d = const_cast<void *>(reference_data);
-        else { if (int rc = pool.alloc(&ref_d, nb)) return rc; CUDA_TRY(cudaMemcpyAsync(ref_d, reference_data, nb, cudaMemcpyHostToDevice, st)); }
+        else { if (int rc = pool.alloc(&ref_d, nb)) return rc; if (int rc = copy_in(ref_d, reference_data)) return rc; }
     }
     for (int k = 0; k < nd && nIt > 0; ++k) {
         for (int s = 0; s < (fused ? 2 : 1); ++s) {
@@ -837,8 +874,12 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     if (p->use_stopping) CUDA_TRY(cudaMallocHost(&pinned, 4 * sizeof(double)));
     struct PinFree { double *p; ~PinFree() { if (p) cudaFreeHost(p); } } pinfree{pinned};
 
+    auto sse = [&](const void *a, const void *b, double *out) -> int {
+        return p->dtype == CYTVDN_F32 ? run_sse<float>(nvox, a, b, out, st, n3, n3p)
+                                      : run_sse<double>(nvox, a, b, out, st, n3, n3p);
+    };
     if (reference_data)
-        if (int rc = cytvdn_sum_square_error(nvox, p->dtype, orig_d, ref_d, sums_d + (size_t)nIt * 4 + 3, st)) return rc;
+        if (int rc = sse(orig_d, ref_d, sums_d + (size_t)nIt * 4 + 3)) return rc;
 
     CUDA_TRY(cudaEventRecord(ev[1], st));
     // iteration 0 reads the reconstruction straight from the input (recon = datacube.copy(),
@@ -864,22 +905,22 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
             if (fused) {
                 if (int rc = cytvdn_fused_iteration(nd, p->shape, p->dtype, orig_d, u_cur, u_out, b[cur], b[1 - cur],
                                                     phase == 0 ? d[cur] : nullptr, phase == 0 ? d[1 - cur] : nullptr,
-                                                    tkr, p->clip, p->lambda_mu, p->bc_mode, s, nullptr, st))
+                                                    tkr, p->clip, p->lambda_mu, p->bc_mode, s, &sopts, st))
                     return rc;
                 cur = 1 - cur;
                 rnext = 1 - rnext;
             } else {
                 if (int rc = cytvdn_accumulator_update_all(nd, p->shape, p->dtype, u_cur, b[0], phase == 0 ? d[0] : nullptr,
                                                            tkr, p->clip, p->isotropic_R, p->isotropic_Q, p->bc_mode, s,
-                                                           nullptr, st))
+                                                           &sopts, st))
                     return rc;
                 if (int rc = cytvdn_datacube_update(nd, p->shape, p->dtype, orig_d, u_cur, u_out, b[0], p->lambda_mu,
-                                                    p->bc_mode, s + 1, nullptr, st))
+                                                    p->bc_mode, s + 1, &sopts, st))
                     return rc;
             }
             u_cur = u_out;
             if (reference_data)
-                if (int rc = cytvdn_sum_square_error(nvox, p->dtype, ref_d, u_cur, s + 3, st)) return rc;
+                if (int rc = sse(ref_d, u_cur, s + 3)) return rc;
             ran[i] = 1;
             ++done[phase];
             if (p->use_stopping) {                              // cyTVDN.py:189-194 / :236-242
@@ -895,7 +936,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         CUDA_TRY(cudaMemcpyAsync(rbuf[0], u_cur, nb, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaEventRecord(ev[2], st));
 
-    if (!recon_dev) CUDA_TRY(cudaMemcpyAsync(recon, rbuf[0], nb, cudaMemcpyDeviceToHost, st));
+    if (!recon_dev) if (int rc = copy_out(recon, rbuf[0])) return rc;
     CUDA_TRY(cudaMemcpyAsync(sums_h.data(), sums_d, nsums * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < nIt; ++i) {

@@ -65,7 +65,7 @@ tv_fused_kernel(const FusedParams<T> P)
         const int64_t e = c.e;
         const int32_t coord[3] = {c.i, c.j, c.k};
         const int32_t extent[3] = {S.n0, S.n1, S.n2};
-        const int64_t stride[3] = {S.st0, S.st1, (int64_t)S.n3};
+        const int64_t stride[3] = {S.st0, S.st1, (int64_t)S.n3p};
 
         // ---------------- addresses (selects, no branches) -----------------------------------------
         int64_t poff[3], yoff[3];
@@ -117,15 +117,19 @@ tv_fused_kernel(const FusedParams<T> P)
             acc_update<T, FISTA>(us.v[v], v == 0 ? left : us.v[v - 1], b3.v[v], FISTA ? d3.v[v] : T(0),
                                  P.clip[3], P.tk, v3.v[v], n3s.v[v]);
         T right3 = __shfl_down_sync(0xffffffffu, n3s.v[0], 1);     // b'_3 of the next voxel on the row
-        if (c.l0 + VW == S.n3) {                                    // row end: wrap to l = 0 (or 0)
-            if (P.zero_wrap & 8) right3 = T(0);
-            else {
-                const int64_t y = e + VW - S.n3;
+        T wrap3 = T(0);                     // b'_3 beyond the row's last voxel: the row's voxel 0 (or 0)
+        if (c.row_end) {
+            if (!(P.zero_wrap & 8)) {
+                const int64_t y = e - c.l0;
                 const T uyy = __ldg(P.uin + y);
-                const T py = (P.bc[3] == 2) ? uyy : us.v[VW - 1];
+                T ulast = us.v[0];                           // the row's last real voxel lives in this vector
+#pragma unroll
+                for (int v = 1; v < VW; ++v)
+                    if (v == c.vl) ulast = us.v[v];
+                const T py = (P.bc[3] == 2) ? uyy : ulast;   // periodic: the voxel before index 0 is the last one
                 T vy;
                 acc_update<T, FISTA>(uyy, py, __ldg(P.bin[3] + y), FISTA ? __ldg(P.din[3] + y) : T(0),
-                                     P.clip[3], P.tk, vy, right3);
+                                     P.clip[3], P.tk, vy, wrap3);
             }
         } else if (lane == 31) {                                    // next vector belongs to another warp
             const int64_t y = e + VW;
@@ -141,8 +145,10 @@ tv_fused_kernel(const FusedParams<T> P)
         Vec<T, VW> term[4];                // w_d (b'_d[x] - b'_d[x+e_d])
 #pragma unroll
         for (int v = 0; v < VW; ++v) {
-            sb += absval(n3s.v[v]);
-            term[3].v[v] = P.w[3] * (n3s.v[v] - (v == VW - 1 ? right3 : n3s.v[v + 1 < VW ? v + 1 : v]));
+            if (v <= c.vl) sb += absval(n3s.v[v]);           // pad voxels of a padded row do not count
+            T fwd = v == VW - 1 ? right3 : n3s.v[v + 1 < VW ? v + 1 : v];
+            if (c.row_end && v == c.vl) fwd = wrap3;
+            term[3].v[v] = P.w[3] * (n3s.v[v] - fwd);
         }
 
         // ---------------- far axes: b'_d at x (stored) and at x + e_d (recomputed, used only here) ----
@@ -159,7 +165,7 @@ tv_fused_kernel(const FusedParams<T> P)
                 acc_update<T, FISTA>(uy[d].v[v], jz0 ? uy[d].v[v] : us.v[v], by[d].v[v], FISTA ? dy[d].v[v] : T(0),
                                      P.clip[d], P.tk, vy, nf);
                 if (zero) nf = T(0);
-                sb += absval(ns.v[v]);
+                if (v <= c.vl) sb += absval(ns.v[v]);
                 term[d].v[v] = P.w[d] * (ns.v[v] - nf);
             }
             if (c.active) {
@@ -177,8 +183,10 @@ tv_fused_kernel(const FusedParams<T> P)
             if (AX2) s = s + term[2].v[v];
             s = s + term[3].v[v];
             un.v[v] = f.v[v] - s;
-            sd += absval(un.v[v] - us.v[v]);
-            so += absval(us.v[v]);
+            if (v <= c.vl) {
+                sd += absval(un.v[v] - us.v[v]);
+                so += absval(us.v[v]);
+            }
         }
         if (c.active) st_stream<T, VW>(P.uout + e, un);
         if (c.owned) {

@@ -127,7 +127,7 @@ tv_fused_tma_kernel(const FusedParams<T> P)
         const int64_t e = c.e;
         const int32_t coord[3] = {c.i, c.j, c.k};
         const int32_t extent[3] = {S.n0, S.n1, S.n2};
-        const int64_t stride[3] = {S.st0, S.st1, (int64_t)S.n3};
+        const int64_t stride[3] = {S.st0, S.st1, (int64_t)S.n3p};
         int64_t poff[3], yoff[3];
         bool at_end[3];
 #pragma unroll

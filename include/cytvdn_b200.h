@@ -66,6 +66,10 @@ int         cytvdn_device_count(int *count);
  *  flags bits 8..11 : axis k (bit 8+k) uses the Jia-Zhao boundary in the accumulator update whatever
  *            bc_mode says.  For periodic runs that are split on axis k: the wrap there is done by the halo
  *            exchange, the block's own index 0 on that axis is an overlap plane.
+ *  row_pitch : all arrays of the call store their rows (fast axis) `row_pitch` elements apart instead of
+ *            densely; the pad voxels are ignored (never read as neighbours of real voxels, excluded from the
+ *            reductions; they are overwritten with unspecified values).  cytvdn_denoise pads rows to the
+ *            vector width internally so that odd row lengths run on the 16-byte path.
  *  l2_budget_bytes : working-set budget that sizes the axis-1 strips of the sweep
  *            (0 = library default).
  */
@@ -77,6 +81,7 @@ typedef struct cytvdn_step_opts {
     int32_t zero_wrap_mask;
     int32_t flags;              /* bit 0: dynamic tile scheduling, bits 8..11: per-axis Jia-Zhao (see below) */
     int64_t l2_budget_bytes;
+    int64_t row_pitch;          /* elements between consecutive rows of the fast axis; 0 = dense (= extent) */
 } cytvdn_step_opts;
 
 /*

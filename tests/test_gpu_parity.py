@@ -552,3 +552,89 @@ def test_fullsize_fused_iteration_equals_two_pass(tv):
     for k in range(4):
         assert torch.equal(B[0][k], b[k]) and torch.equal(D[0][k], d[k])
     np.testing.assert_allclose(sf.cpu().numpy()[:, :3], s2.cpu().numpy()[:, :3], rtol=1e-7)   # fp32 partials of <=16 values
+
+
+@pytest.mark.parametrize("pad", ["1", "0"])
+@pytest.mark.parametrize("schedule", ["fused", "two_pass"])
+@pytest.mark.parametrize("shape,dt,kw", [
+    ((6, 7, 9, 11), "float32", dict(iterations=15, FISTA=True)),
+    ((6, 7, 9, 13), "float32", dict(iterations=15, FISTA=True, BC_mode=0)),
+    ((5, 4, 6, 130), "float32", dict(iterations=[6, 5])),
+    ((6, 5, 7, 9), "float64", dict(iterations=12, FISTA=True, BC_mode=0)),
+    ((4, 5, 6, 7), "float32", dict(iterations=8, FISTA=True, isotropic_R=True, isotropic_Q=True)),
+    ((3, 4, 5, 1), "float32", dict(iterations=6, FISTA=True)),
+    ((3, 4, 5, 2), "float32", dict(iterations=6, FISTA=False, BC_mode=0)),
+])
+def test_odd_rows_padded_internally(tv, O, shape, dt, kw, schedule, pad, monkeypatch):
+    """Rows that are not a multiple of the vector width: cytvdn_denoise pads them internally (16-byte path);
+    CYTVDN_PAD_ROWS=0 keeps the dense scalar / 8-byte paths.  Same results either way, also with reference_data."""
+    iso = kw.get("isotropic_R")
+    if iso and schedule == "fused":
+        pytest.skip("fused covers the anisotropic update only")
+    monkeypatch.setenv("CYTVDN_PAD_ROWS", pad)
+    monkeypatch.setenv("CYTVDN_SCHEDULE", schedule)
+    rng = np.random.default_rng(abs(hash((shape, dt))) % 2**32)
+    data = counts(rng, shape, dt)
+    refd = counts(rng, shape, dt)
+    mu = np.array([1, 1, .5, .5], dtype=dt)
+    ref = O.denoise4D(data, mu, quiet=True, reference_data=refd, kernels=O.PortKernels("D"), scalars="D", **kw)
+    out = tv.denoise4D(data, mu, quiet=True, reference_data=refd, **kw)
+    if iso:
+        assert float(np.abs(out[0] - ref[0]).max()) <= _tol(dt, data)
+    else:
+        assert np.array_equal(out[0], ref[0]), f"max diff {np.abs(out[0] - ref[0]).max()}"
+    np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
+    np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR, atol=1e-30)
+    np.testing.assert_allclose(out[3].astype(np.float64), ref[3], rtol=RTOL_SCALAR)
+    # device tensors in / out take the same route (2-D device copies)
+    import torch
+    t = torch.from_numpy(data).cuda()
+    o2 = tv.denoise4D(t, mu, quiet=True, **kw)
+    assert torch.equal(o2[0].cpu(), torch.from_numpy(out[0]))
+
+
+def test_step_functions_with_row_pitch(tv, O):
+    """cytvdn_step_opts.row_pitch: arrays whose rows are stored `pitch` elements apart (pads are ignored)."""
+    import ctypes as C
+    import torch
+    from cytvdn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(77)
+    shape, pitch = (5, 6, 7, 10), 12
+    a = counts(rng, shape, "float32")
+    bs = [rng.normal(0, 20, shape).astype(np.float32) for _ in range(4)]
+    ds = [rng.normal(0, 20, shape).astype(np.float32) for _ in range(4)]
+    K = O.PortKernels("D")
+
+    def padded(x):
+        t = torch.full(shape[:3] + (pitch,), float("nan"), dtype=torch.float32, device="cuda")   # NaN pads must stay inert
+        t[..., :shape[3]] = torch.from_numpy(x).cuda()
+        return t
+    ta, tb, td = padded(a), [padded(x) for x in bs], [padded(x) for x in ds]
+    o = _lib.StepOpts()
+    o.row_pitch = pitch
+    sh = (C.c_int64 * 4)(*shape)
+    st = torch.cuda.current_stream().cuda_stream
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+    clip = (C.c_double * 4)(32, 32, 64, 64)
+    ptr = lambda ts: (C.c_void_p * 4)(*[t.data_ptr() for t in ts])
+    _lib.check(lib.cytvdn_accumulator_update_all(4, sh, 0, ta.data_ptr(), ptr(tb), ptr(td), 0.3, clip, 0, 0, 2,
+                                                 sums.data_ptr(), C.byref(o), st))
+    want = 0.0
+    for ax in range(4):
+        want += K.accumulator_update(a, bs[ax], ds[ax], 0.3, ax, [32, 32, 64, 64][ax], 2)
+    torch.cuda.synchronize()
+    for ax in range(4):
+        assert np.array_equal(tb[ax][..., :shape[3]].cpu().numpy(), bs[ax])
+        assert np.array_equal(td[ax][..., :shape[3]].cpu().numpy(), ds[ax])
+    assert float(sums[0]) == pytest.approx(want, rel=1e-6)
+    w = np.array([1 / 32, 1 / 32, 1 / 64, 1 / 64], np.float32)
+    u = a + rng.normal(0, 3, shape).astype(np.float32)
+    tu = padded(u)
+    wd = (C.c_double * 4)(*[float(x) for x in w])
+    _lib.check(lib.cytvdn_datacube_update(4, sh, 0, ta.data_ptr(), tu.data_ptr(), tu.data_ptr(), ptr(tb), wd, 0,
+                                          sums.data_ptr(), C.byref(o), st))
+    s_want = K.datacube_update_sums(a, u, bs, w, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(tu[..., :shape[3]].cpu().numpy(), u)
+    assert float(sums[0]) == pytest.approx(s_want[0], rel=1e-6) and float(sums[1]) == pytest.approx(s_want[1], rel=1e-6)
