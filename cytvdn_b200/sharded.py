@@ -321,8 +321,15 @@ class CudaShard:
         _lib.require_gpu()
         assert tuple(shard.shape) == tuple(plan.local_shape), (tuple(shard.shape), plan.local_shape)
         assert shard.is_cuda and shard.is_contiguous() and shard.dtype in (torch.float32, torch.float64)
-        self.plan, self.orig, self.fista = plan, shard, fista
         dt = np.float32 if shard.dtype == torch.float32 else np.float64
+        # rows that are not a multiple of the 16-byte vector width are padded in the device state
+        # (cytvdn_step_opts.row_pitch), as cytvdn_denoise does, so that every shape runs on the vector path
+        self.n3 = int(shard.shape[3])
+        vwf = 16 // (4 if dt == np.float32 else 8)
+        self.n3p = (self.n3 + vwf - 1) // vwf * vwf
+        if self.n3p != self.n3:
+            shard = torch.nn.functional.pad(shard, (0, self.n3p - self.n3)).contiguous()
+        self.plan, self.orig, self.fista = plan, shard, fista
         mu = np.asarray(mu, dtype=dt)
         lam = (mu * 1.0 / 32.0) if lam is None else np.asarray(lam, dtype=dt)      # cyTVDN.py:67-68
         self.clip = (C.c_double * 4)(*[float(v) for v in (1.0 / lam)])
@@ -373,6 +380,7 @@ class CudaShard:
     def _opts(self, box0=None, dynamic=False):
         o = self._lib.StepOpts()
         o.flags = (1 if dynamic else 0) | self.plan.jz_flags
+        o.row_pitch = self.n3p
         n0 = self.plan.local_shape[0]
         o.box_lo[0], o.box_hi[0] = (0, n0) if box0 is None else box0
         o.box_lo[1], o.box_hi[1] = 0, 0
@@ -398,6 +406,10 @@ class CudaShard:
             4, self.sh, self.code, self.orig.data_ptr(), self.recon.data_ptr(), self.recon.data_ptr(), self.bp,
             self.w, self.bc_mode, out, C.byref(o), st))
         self.launches += 1
+
+    def result(self):
+        """The current reconstruction of the local block without the row padding."""
+        return self.recon if self.n3p == self.n3 else self.recon[..., :self.n3]
 
     # slot layout per iteration: A launches 0..3 (1 double each), B launches 4.. (2 doubles each)
     def local_sums(self):
@@ -576,8 +588,8 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
         delta = np.where(ran, g[:n, 1] / g[:n, 2], 0.0).astype(dt)
     torch.cuda.current_stream(shard.device).synchronize()
     if return_state:
-        return sh.recon, b_norm, delta, sh
-    return sh.recon, b_norm, delta
+        return sh.result(), b_norm, delta, sh
+    return sh.result(), b_norm, delta
 
 
 # ------------------------------------------------------------------------------------------------
@@ -679,7 +691,7 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
     out = torch.empty_like(gdata)
     tot = torch.zeros((max(n, 1), 3), dtype=torch.float64, device=gdata.device)
     for s in shards:
-        out[s.plan.owned_global] = s.recon[s.plan.owned_local]
+        out[s.plan.owned_global] = s.result()[s.plan.owned_local]
         tot += s.fused_local_sums() if fused else s.local_sums()
     g = tot.cpu().numpy()
     with np.errstate(all="ignore"):

@@ -499,6 +499,21 @@ def test_sharded_periodic_equals_single_gpu(tv, world, grid, split, schedule):
     np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
 
 
+@pytest.mark.parametrize("schedule", ["two_pass", "fused"])
+def test_sharded_odd_rows(tv, schedule):
+    """Row length 13: the sharded driver pads its device state like cytvdn_denoise does."""
+    import torch
+    from cytvdn_b200 import sharded
+    rng = np.random.default_rng(55)
+    data = counts(rng, (11, 6, 7, 13), "float32")
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = tv.denoise4D(data, mu, 9, True, quiet=True)
+    got, bn, dl = sharded.emulate_on_one_device(torch.from_numpy(data).cuda(), mu, 3, None, 9, True, True, schedule=schedule)
+    assert got.shape == data.shape and np.array_equal(got.cpu().numpy(), ref[0])
+    np.testing.assert_allclose(bn, ref[1].astype(np.float64), rtol=1e-5)
+    np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
+
+
 def test_sharded_generator_is_shard_invariant(tv):
     """The device generator yields the same global array whatever the sharding, and equals its
     NumPy mirror bit for bit (so the CPU reference can consume the identical input)."""
@@ -638,3 +653,39 @@ def test_step_functions_with_row_pitch(tv, O):
     torch.cuda.synchronize()
     assert np.array_equal(tu[..., :shape[3]].cpu().numpy(), u)
     assert float(sums[0]) == pytest.approx(s_want[0], rel=1e-6) and float(sums[1]) == pytest.approx(s_want[1], rel=1e-6)
+
+
+def test_fuzz_shapes_and_options_vs_oracle(tv, O, monkeypatch):
+    """Seeded random sweep over shapes (incl. tiny / odd / long rows), dtypes, boundary modes, schedules, strip
+    budgets, iteration mixes: recon bit-exact against the oracle, scalars within 1e-4."""
+    rng = np.random.default_rng(20261018)
+    n_cases = 0
+    for case in range(60):
+        nd = int(rng.choice([3, 4]))
+        if nd == 4:
+            shape = tuple(int(v) for v in (rng.integers(1, 9), rng.integers(1, 9), rng.integers(1, 12), rng.integers(1, 70)))
+        else:
+            shape = tuple(int(v) for v in (rng.integers(1, 10), rng.integers(1, 10), rng.integers(1, 300)))
+        dt = str(rng.choice(["float32", "float64"]))
+        bc = int(rng.choice([0, 2]))
+        fista = bool(rng.integers(0, 2))
+        iters = int(rng.integers(1, 12))
+        if rng.random() < 0.25:
+            iters = [int(rng.integers(0, 6)), int(rng.integers(0, 6))]
+        sched = str(rng.choice(["fused", "two_pass"]))
+        monkeypatch.setenv("CYTVDN_SCHEDULE", sched)
+        monkeypatch.setenv("CYTVDN_L2_BUDGET_MB", str(float(rng.choice([0.001, 0.01, 0.1, 24]))))
+        monkeypatch.setenv("CYTVDN_PAD_ROWS", str(int(rng.integers(0, 2))))
+        data = counts(rng, shape, dt)
+        mu = np.array([1, 1, .5, .5][:nd] if nd == 4 else [1, 1, .5], dtype=dt)
+        fo, fg = (O.denoise4D, tv.denoise4D) if nd == 4 else (O.denoise3D, tv.denoise3D)
+        ref = fo(data, mu, iterations=iters, FISTA=fista, BC_mode=bc, quiet=True, kernels=O.PortKernels("D"), scalars="D")
+        out = fg(data, mu, iterations=iters, FISTA=fista, BC_mode=bc, quiet=True)
+        tag = f"case {case}: {shape} {dt} bc={bc} fista={fista} iters={iters} {sched}"
+        assert np.array_equal(out[0], ref[0]), tag
+        with np.errstate(all="ignore"):
+            np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR, err_msg=tag)
+            ok = np.isfinite(ref[2])
+            np.testing.assert_allclose(out[2].astype(np.float64)[ok], ref[2][ok], rtol=RTOL_SCALAR, atol=1e-30, err_msg=tag)
+        n_cases += 1
+    assert n_cases == 60
