@@ -295,17 +295,20 @@ def run_single(args):
     traffic = committed_traffic()
     eq96 = (BYTES_A + BYTES_B) * vox / (ms_per_step * 1e-3) / 1e9
     if fused:
-        ach = BYTES_FUSED * vox / (a_ms * 1e-3) / 1e9
+        # a fused single pass is still reported against the 96 B/voxel contract figure of
+        # the two-pass iteration, with the variant stated; what the kernel really moves is 76 B/voxel.
+        ach = (BYTES_A + BYTES_B) * vox / (a_ms * 1e-3) / 1e9
+        moved = BYTES_FUSED * vox / (a_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm",
-                    "kernel": "tv_fused_kernel<float,4,FISTA,4D> (whole iteration in one pass, 76 B/voxel: every array "
-                              "crosses HBM once)",
+                    "kernel": "tv_fused_kernel<float,4,FISTA,4D> (whole iteration = half-steps A+B in one pass)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic.get("tv_fused_kernel"), "peak_source": peak_src, "ms_per_launch": a_ms,
-                    "bytes_per_voxel": BYTES_FUSED,
-                    "two_pass_equivalent": {"bytes_per_voxel": BYTES_A + BYTES_B, "GB/s": eq96,
-                                            "frac_of_measured": eq96 / peak, "frac_of_8TBs_nominal": eq96 / 8000.0,
-                                            "note": "throughput expressed in the 96 B/voxel two-pass contract figure "
-                                                    "(SURVEY 8d); the fused kernel moves 76 B/voxel"}}
+                    "bytes_per_voxel": BYTES_A + BYTES_B,
+                    "variant": "fused single pass: the contract's 96 B/voxel of work (SURVEY 8d) is done while moving "
+                               "76 B/voxel (every array crosses HBM once), hence frac > 1; see `moved`",
+                    "moved": {"bytes_per_voxel": BYTES_FUSED, "GB/s": moved, "frac": moved / peak,
+                              "frac_of_8TBs_nominal": moved / 8000.0},
+                    "frac_of_8TBs_nominal": ach / 8000.0}
     else:
         ach_a = BYTES_A * vox / (a_ms * 1e-3) / 1e9
         ach_b = BYTES_B * vox / (b_ms * 1e-3) / 1e9

@@ -141,103 +141,13 @@ __device__ __forceinline__ void st_stream(T *p, const Vec<T, VW> &x)
     u.v = x;
     __stcs(reinterpret_cast<typename Raw<T, VW>::type *>(p), u.r);
 }
-// Read-only, touched once: non-coherent path, no L1 allocation, L2 evict-first policy.  Not volatile:
-// the compiler may hoist these above stores (the fused kernel never writes what it reads).
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
+// L2 policy descriptor (only the experimental TMA variant passes one explicitly; the product kernels keep the
+// default policy on every read: descriptor-carrying loads and evict-first hints were measured slower)
 __device__ __forceinline__ uint64_t l2_policy_evict_normal()
 {
     uint64_t p;
     asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
     return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-// same, but allocating in L1 (default L1 policy)
-__device__ __forceinline__ float4 ldg_nc_hint(const float4 *p, uint64_t pol)
-{
-    float4 r;
-    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ float2 ldg_nc_hint(const float2 *p, uint64_t pol)
-{
-    float2 r;
-    asm("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ double2 ldg_nc_hint(const double2 *p, uint64_t pol)
-{
-    double2 r;
-    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ float ldg_nc_hint(const float *p, uint64_t pol)
-{
-    float r;
-    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ double ldg_nc_hint(const double *p, uint64_t pol)
-{
-    double r;
-    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
-    return r;
-}
-template <typename T, int VW>
-__device__ __forceinline__ Vec<T, VW> ld_ro_hint(const T *p, uint64_t pol)
-{
-    VecU<T, VW> u;
-    u.r = ldg_nc_hint(reinterpret_cast<const typename Raw<T, VW>::type *>(p), pol);
-    return u.v;
-}
-__device__ __forceinline__ float4 ldg_nc_stream(const float4 *p, uint64_t pol)
-{
-    float4 r;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ float2 ldg_nc_stream(const float2 *p, uint64_t pol)
-{
-    float2 r;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ double2 ldg_nc_stream(const double2 *p, uint64_t pol)
-{
-    double2 r;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
-        : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ float ldg_nc_stream(const float *p, uint64_t pol)
-{
-    float r;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ double ldg_nc_stream(const double *p, uint64_t pol)
-{
-    double r;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
-    return r;
-}
-template <typename T, int VW>
-__device__ __forceinline__ Vec<T, VW> ld_ro_stream(const T *p, uint64_t pol)
-{
-    VecU<T, VW> u;
-    u.r = ldg_nc_stream(reinterpret_cast<const typename Raw<T, VW>::type *>(p), pol);
-    return u.v;
 }
 
 // Neighbour loads that must be ISSUED AFTER the barrier that precedes them in the source: coherent
