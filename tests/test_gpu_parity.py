@@ -689,3 +689,35 @@ def test_fuzz_shapes_and_options_vs_oracle(tv, O, monkeypatch):
             np.testing.assert_allclose(out[2].astype(np.float64)[ok], ref[2][ok], rtol=RTOL_SCALAR, atol=1e-30, err_msg=tag)
         n_cases += 1
     assert n_cases == 60
+
+
+# ------------------------------------------------------------------------------------------------
+# (5) north_star's acceptance check at the sizes SURVEY 8d names: 100 iterations against the compiled,
+#     UNMODIFIED reference kernels (oracle/_ref) when they are present, else against the pinned C port
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,dt,tol_scale", [((32, 32, 64, 64), "float32", 1e-4), ((16, 16, 64, 64), "float64", None)])
+def test_100_iterations_vs_reference_kernels(tv, O, shape, dt, tol_scale):
+    from cytvdn_b200 import synth
+    data = synth.stem4d_poisson(shape, seed=2, counts=500.0, dtype=dt)
+    mu = np.array([1, 1, .5, .5], dtype=dt)
+    K = O.default_kernels("D")                      # reference kernels if built (any thread count: anisotropic)
+    ref = O.denoise4D(data, mu, 100, True, quiet=True, kernels=K, scalars="D")
+    for sched in ("fused", "two_pass"):
+        out = tv.denoise4D(data, mu, 100, True, quiet=True, schedule=sched)
+        err = float(np.abs(out[0].astype(np.float64) - ref[0].astype(np.float64)).max())
+        rng_ = float(data.max() - data.min())
+        assert err <= (tol_scale * rng_ if tol_scale else 1e-10), (K.name, sched, err)    # north_star's tolerance
+        assert err == 0.0, (K.name, sched, err)                                            # and in fact bit-exact
+        np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
+        np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR)
+
+
+def test_100_iterations_half_isotropic_vs_oracle(tv, O):
+    from cytvdn_b200 import synth
+    data = synth.stem4d_poisson((16, 16, 64, 64), seed=2, counts=500.0)
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = O.denoise4D(data, mu, 100, True, None, True, True, quiet=True, kernels=O.PortKernels("D"), scalars="D")
+    out = tv.denoise4D(data, mu, 100, True, isotropic_R=True, isotropic_Q=True, quiet=True)
+    assert float(np.abs(out[0] - ref[0]).max()) <= 1e-4 * float(data.max() - data.min())
+    np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
+    np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR)
