@@ -721,3 +721,26 @@ def test_100_iterations_half_isotropic_vs_oracle(tv, O):
     assert float(np.abs(out[0] - ref[0]).max()) <= 1e-4 * float(data.max() - data.min())
     np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
     np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR)
+
+
+def test_verbose_output_and_check_memory(tv, capsys):
+    """quiet=False prints the reference's information lines (lambda/mu, memory need) and must not fail;
+    the step functions return Python floats like the Cython kernels."""
+    data = np.full((4, 4, 8, 8), 7.0, np.float32)
+    data[1, 2, 3, 4] = 90.0
+    mu = np.array([1, 1, .5, .5], np.float32)
+    tv.denoise4D(data, mu, 3, True)
+    out = capsys.readouterr().out
+    assert "λ/μ ≈ [1/32, 1/32, 1/32, 1/32]" in out and "GPU memory" in out and "FISTA Accelerated" in out
+    tv.denoise4D(data, mu, 3, False, lam=mu / 16)          # lam/mu > 1/32: the 4-D driver only warns (cyTVDN.py:89-90)
+    assert "WARNING: Parameters must satisfy" in capsys.readouterr().out
+    tv.denoise3D(data[0], mu[:3], 3)
+    assert "Unaccelerated TV denoising will require" in capsys.readouterr().out
+    need = tv.check_memory(data)
+    assert need["Anisotropic FISTA"] == data.nbytes * 10 and "Datacube size" in capsys.readouterr().out
+    r = tv.accumulator_update_4D(data, np.zeros_like(data), 0, 32.0)
+    assert type(r) is float
+    r = tv.datacube_update_4D(data, data.copy(), *[np.zeros_like(data)] * 4, np.full(4, 1 / 32, np.float32))
+    assert type(r) is float and r == 0.0
+    tv.denoise4D(data, mu, 30, False, 0.5, quiet=False)     # unaccelerated early stop prints the reference's message
+    assert "Stopping condition reached after" in capsys.readouterr().out
