@@ -45,7 +45,11 @@ template <typename T, int VW, bool FISTA, bool AX2>
 #ifndef FUSED_MINB
 #define FUSED_MINB 2
 #endif
-__global__ void __launch_bounds__(kBlock, FUSED_MINB)
+#ifndef FUSED_MINB_PLAIN
+#define FUSED_MINB_PLAIN 3      // 3-D unaccelerated variant: few arrays, 3 CTAs per SM fit without spills (measured
+                                // +17..60 %); the 4-D unaccelerated variant would spill and was measured slower
+#endif
+__global__ void __launch_bounds__(kBlock, ((!FISTA && !AX2) ? FUSED_MINB_PLAIN : FUSED_MINB))
 tv_fused_kernel(const FusedParams<T> P)
 {
     const Sweep &S = P.S;
