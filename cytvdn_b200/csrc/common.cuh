@@ -14,7 +14,10 @@
 
 namespace cytvdn {
 
-constexpr int kBlock = 256;            // threads per CTA
+#ifndef CYTVDN_BLOCK
+#define CYTVDN_BLOCK 256
+#endif
+constexpr int kBlock = CYTVDN_BLOCK;   // threads per CTA (= vectors per tile)
 constexpr int kWarps = kBlock / 32;
 
 // ---- division of n < 2^31 by a runtime constant ------------------------------------------
