@@ -779,6 +779,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     Dims D;
     if (int rc = validate_params(p, &D)) return rc;
     if (!data || !recon) return fail(CYTVDN_E_INVALID, "data / recon is NULL");
+    if (data == recon) return fail(CYTVDN_E_INVALID, "recon must not alias data (the input is read in every iteration)");
     const int nF = p->iters_fista, nU = p->iters_plain, nIt = nF + nU;
     if (nIt > 0 && (!bnorm || !delta)) return fail(CYTVDN_E_INVALID, "bnorm / delta is NULL");
     if (reference_data && !mse) return fail(CYTVDN_E_INVALID, "mse is NULL but reference_data was given");

@@ -154,10 +154,14 @@ def test_c_abi_argument_validation_without_gpu():
     P.iters_fista = -1
     assert lib.cytvdn_denoise(C.byref(P), one, one, None, None, None, None, None, None) == 1
     assert "negative iteration count" in err()
-    P.iters_fista, P.bc_mode = 2, 1
-    assert lib.cytvdn_denoise(C.byref(P), one, one, None, None, None, None, None, None) == 4
-    P.bc_mode, P.ndim, P.isotropic_R = 2, 3, 1
+    P.iters_fista = 2
     assert lib.cytvdn_denoise(C.byref(P), one, one, None, None, None, None, None, None) == 1
+    assert "alias" in err()
+    two = C.c_void_p(32)
+    P.bc_mode = 1
+    assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 4
+    P.bc_mode, P.ndim, P.isotropic_R = 2, 3, 1
+    assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 1
     assert "4-D only" in err()
     n = C.c_int64(0)
     P.ndim, P.isotropic_R, P.iters_fista, P.iters_plain = 4, 0, 10, 0
