@@ -171,3 +171,24 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.cytvdn_denoise_workspace_bytes(C.byref(P), 0, 0, C.byref(n)) == 0
     assert n.value == (8 + 2) * 4 * 256                # two-pass from host data: b, d, orig, recon
     assert lib.cytvdn_launch_count() >= 0
+
+
+def _build_c_example(tmp_path):
+    exe = str(tmp_path / "denoise_c_abi")
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    lib = os.path.join(ROOT, "cytvdn_b200")
+    subprocess.run([gcc, os.path.join(ROOT, "examples", "denoise_c_abi.c"), "-I", os.path.join(ROOT, "include"), "-L", lib,
+                    "-lcytvdn_b200", f"-Wl,-rpath,{lib}", "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_c_example_links_against_the_c_abi(tmp_path):
+    """A plain C host compiles against include/cytvdn_b200.h and links the shared library."""
+    out = subprocess.run([_build_c_example(tmp_path)], check=True, capture_output=True, text=True).stdout
+    assert "cytvdn ABI version 100" in out
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_gpu(tmp_path):
+    out = subprocess.run([_build_c_example(tmp_path)], check=True, capture_output=True, text=True).stdout
+    assert "20 FISTA iterations" in out and "schedule 2" in out
