@@ -51,7 +51,7 @@ def build_parser():
     p.add_argument("-p", "--dataset", default=None, help="HDF5 dataset path (h5/emd input)")
     p.add_argument("--stop", type=float, default=None, help="stopping_relative_change")
     p.add_argument("--grid", default="1d", choices=["1d", "mpi"], help="tile layout: axis-0 split or mpi.py's (wx, wy)")
-    p.add_argument("--schedule", default="fused", choices=["fused", "two_pass"])
+    p.add_argument("--schedule", default="auto", choices=["auto", "fused", "two_pass"])
     return p
 
 
@@ -127,7 +127,7 @@ def main(argv=None):
         block = torch.from_numpy(read_block(data, tuple(slice(None) for _ in range(ndim)))).to(dev)
         fn = tv.denoise4D if ndim == 4 else tv.denoise3D
         kw = dict(iterations=iterations, FISTA=fista, stopping_relative_change=args.stop, lam=lam, quiet=True,
-                  schedule=args.schedule)
+                  schedule=None if args.schedule == "auto" else args.schedule)
         recon, bn, dl = fn(block, mu, **kw)
         out = create_output(args.output[0], data.shape)
         out[...] = recon.cpu().numpy()

@@ -548,7 +548,8 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
     ``recon_local[plan.owned_local]`` is this rank's part of the result and the two 1-D arrays are the
     global values (owned-voxel sums, all-reduced).  ``iterations`` may be ``[n_FISTA, n_plain]``.
     ``schedule``: ``"fused"`` (one pass and one exchange per iteration, needs a second set of
-    accumulator arrays) or ``"two_pass"`` (the reference's structure: two sweeps, two exchanges).
+    accumulator arrays), ``"two_pass"`` (the reference's structure: two sweeps, two exchanges) or ``None`` /
+    ``"auto"``: fused when the second state set fits on every rank.
     Boundary: Jia-Zhao (``BC_mode=2``) or, with a ``ShardPlan(..., periodic=True)``, periodic (``BC_mode=0``).
     """
     import torch
@@ -561,6 +562,15 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
         nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
     n = nF + nU
     world = plan.world
+    if schedule in (None, "auto"):
+        # fused needs 1 + 2*(1 + 4*(1 or 2)) arrays next to the caller's shard; two_pass 1 + 4*(1 or 2)
+        per = 4 * (2 if nF > 0 else 1)
+        free_b, _ = torch.cuda.mem_get_info(shard.device)
+        need = (1 + 2 * (1 + per)) * shard.numel() * shard.element_size()
+        fits = torch.tensor([1 if need + (1 << 30) < free_b else 0], device=shard.device)
+        if world > 1:
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=group)      # every rank must take the same schedule
+        schedule = "fused" if int(fits.item()) else "two_pass"
     fused = schedule == "fused"
     sh = CudaShard(plan, shard, mu, lam, fista=nF > 0, n_iter=n, fused=fused)
     one_d = plan.grid[1] == 1
