@@ -744,3 +744,47 @@ def test_verbose_output_and_check_memory(tv, capsys):
     assert type(r) is float and r == 0.0
     tv.denoise4D(data, mu, 30, False, 0.5, quiet=False)     # unaccelerated early stop prints the reference's message
     assert "Stopping condition reached after" in capsys.readouterr().out
+
+
+def test_config5_shape_sharded_over_1_2_4_8_ranks(tv):
+    """SURVEY 8d, config 5 parity size (64 x 64 x 32 x 32): every shard count gives the single-GPU result."""
+    import torch
+    from cytvdn_b200 import sharded, synth
+    g = (64, 64, 32, 32)
+    data = synth.stem4d_device(g, seed=2, counts=500.0)
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = tv.denoise4D(data, mu, 10, True, quiet=True)
+    for world, grid in ((1, None), (2, None), (4, None), (8, None), (8, "mpi"), (4, (2, 2))):
+        for sched in ("fused", "two_pass"):
+            got, bn, dl = sharded.emulate_on_one_device(data, mu, world, grid, 10, True, True, schedule=sched)
+            assert torch.equal(got, ref[0]), (world, grid, sched)
+            np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["c2_3d_fista", "c3_4d_fista", "c4_4d_iso"])
+def test_config_shapes_vs_reference_kernels(tv, O, case):
+    """SURVEY 8d parity sizes for configs 2-4: 3-D 64x64x2048 and 4-D 32x32x128x128 (same inner axes as the
+    full configs), against the compiled reference kernels where they can be used (anisotropic: any thread count)."""
+    from cytvdn_b200 import synth
+    if case == "c2_3d_fista":
+        data = synth.eels_cube((64, 64, 2048), seed=1, dose=2.0, gain=8.0)
+        mu = np.array([1, 1, .5], np.float32)
+        ref = O.denoise3D(data, mu, 30, FISTA=True, quiet=True, kernels=O.default_kernels("D"), scalars="D")
+        out = tv.denoise3D(data, mu, 30, FISTA=True, quiet=True)
+        # and the stopping criterion of config 2 stops at the same iteration
+        r2 = O.denoise3D(data, mu, 100, 0.05, 2, True, quiet=True, kernels=O.default_kernels("D"), scalars="D")
+        o2 = tv.denoise3D(data, mu, 100, 0.05, 2, True, quiet=True)
+        assert np.count_nonzero(o2[2]) == np.count_nonzero(r2[2]) and np.array_equal(o2[0], r2[0])
+    else:
+        data = synth.stem4d_poisson((32, 32, 128, 128), seed=2, counts=500.0)
+        mu = np.array([1, 1, .5, .5], np.float32)
+        iso = case == "c4_4d_iso"
+        K = O.PortKernels("D") if iso else O.default_kernels("D")
+        ref = O.denoise4D(data, mu, 40, True, None, iso, iso, quiet=True, kernels=K, scalars="D")
+        out = tv.denoise4D(data, mu, 40, True, isotropic_R=iso, isotropic_Q=iso, quiet=True)
+    if case == "c4_4d_iso":
+        assert float(np.abs(out[0] - ref[0]).max()) <= 1e-4 * float(data.max() - data.min())
+    else:
+        assert np.array_equal(out[0], ref[0])
+    np.testing.assert_allclose(out[1].astype(np.float64), ref[1], rtol=RTOL_SCALAR)
+    np.testing.assert_allclose(out[2].astype(np.float64), ref[2], rtol=RTOL_SCALAR)
