@@ -35,7 +35,7 @@ def run_sharded(args):
         n_total = args.warmup + args.steps
         fused = args.schedule == "fused"
         sh = sharded.CudaShard(plan, x, mu, None, fista=True, n_iter=n_total, fused=fused)
-        comm_stream = torch.cuda.Stream(device=dev) if os.environ.get("CYTVDN_SHARD_OVERLAP", "1") != "0" else None
+        comm_stream = torch.cuda.Stream(device=dev)       # used only with CYTVDN_SHARD_EXCHANGE=overlap
         tk = 1.0
         it = 0
 
@@ -45,8 +45,7 @@ def run_sharded(args):
             if fused:
                 sharded._run_iteration_fused(sh, it, tkr, True, None, comm_stream)
             else:
-                (sharded._run_iteration_overlapped(sh, it, tkr, True, None, comm_stream) if comm_stream is not None
-                 else sharded._run_iteration_simple(sh, it, tkr, True, None))
+                sharded._run_iteration_overlapped(sh, it, tkr, True, None, comm_stream)
             it += 1
 
         for _ in range(args.warmup):
