@@ -384,6 +384,9 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
         if reference_data is not None:
             keep = reference_data if (_is_torch(reference_data) and reference_data.is_cuda) else \
                 torch.as_tensor(np.asarray(reference_data), device=datacube.device)
+            keep = keep.to(device=datacube.device, dtype=datacube.dtype).contiguous()
+            if tuple(keep.shape) != tuple(datacube.shape):
+                raise ValueError("reference_data must have the shape of datacube")
             ref_p = keep.data_ptr()
         else:
             ref_p = None
@@ -393,6 +396,8 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
         data_p, recon_p = datacube.ctypes.data, recon.ctypes.data
         if reference_data is not None:
             keep = np.ascontiguousarray(reference_data, dtype=dt)
+            if keep.shape != datacube.shape:
+                raise ValueError("reference_data must have the shape of datacube")
             ref_p = keep.ctypes.data
         else:
             keep, ref_p = None, None
