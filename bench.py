@@ -212,7 +212,7 @@ def run_single(args):
     torch.cuda.set_device(0)
     shape = tuple(args.shape) if args.shape else SHAPE_1GPU
     vox = int(np.prod(shape))
-    fused = args.schedule == "fused"
+    fused = args.schedule in ("fused", "peer")       # "peer" only differs in how shards talk; one GPU has no peers
     x = synth.stem4d_device(shape, seed=2, counts=500.0)
     nset = 2 if fused else 1
     # --skew: offset the k-th state array by k * SKEW bytes (experiment: power-of-two array sizes showed no
@@ -337,7 +337,7 @@ def run_single(args):
         tm = {}
         t0 = time.perf_counter()
         tv.denoise4D(host_in, mu, iterations=iters, FISTA=True, quiet=True, out=host_out, timing=tm,
-                     schedule=args.schedule)
+                     schedule="fused" if fused else "two_pass")
         dt = time.perf_counter() - t0
         nbytes = vox * 4
         e2e = {"value": vox * iters / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes / iters,
@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--skew", type=int, default=0, help="byte skew between consecutive state arrays (experiment knob)")
-    ap.add_argument("--schedule", default="fused", choices=["fused", "two_pass"],
+    ap.add_argument("--schedule", default="fused", choices=["fused", "two_pass", "peer"],
                     help="fused: one pass per iteration (76 B/voxel); two_pass: half-steps A and B (96 B/voxel)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -33,8 +33,16 @@ def run_sharded(args):
         x = synth.stem4d_device(gshape, offset0=plan.read[0][0], lshape0=n0, seed=2, counts=500.0, device=dev)
         mu = np.array(MU, dtype=np.float32)
         n_total = args.warmup + args.steps
-        fused = args.schedule == "fused"
-        sh = sharded.CudaShard(plan, x, mu, None, fista=True, n_iter=n_total, fused=fused)
+        fused = args.schedule in ("fused", "peer")
+        peer = args.schedule == "peer"
+        if peer:      # owned planes only; the halo is read from the neighbours' HBM inside the fused kernel
+            own = x[plan.owned_local[0]].contiguous()
+            del x
+            torch.cuda.empty_cache()
+            x = own
+            sh = sharded.PeerShard(plan, own, mu, None, fista=True, n_iter=n_total)
+        else:
+            sh = sharded.CudaShard(plan, x, mu, None, fista=True, n_iter=n_total, fused=fused)
         comm_stream = torch.cuda.Stream(device=dev)       # used only with CYTVDN_SHARD_EXCHANGE=overlap
         tk = 1.0
         it = 0
@@ -42,7 +50,9 @@ def run_sharded(args):
         def step():
             nonlocal tk, it
             tkr, tk = sharded.fista_ratio(tk)
-            if fused:
+            if peer:
+                sh.step(it, tkr, True)
+            elif fused:
                 sharded._run_iteration_fused(sh, it, tkr, True, None, comm_stream)
             else:
                 sharded._run_iteration_overlapped(sh, it, tkr, True, None, comm_stream)
@@ -75,11 +85,11 @@ def run_sharded(args):
         clk = clocks.stop() if clocks else None
         gvox = int(np.prod(gshape))
         value = gvox * args.steps / (total_ms * 1e-3) / 1e9
-        glob = (sh.fused_local_sums() if fused else sh.local_sums()).clone()
+        glob = (sh.sums[:, :3] if peer else sh.fused_local_sums() if fused else sh.local_sums()).clone()
         dist.all_reduce(glob)
         last = glob[it - 1].cpu().numpy()
         peak, peak_src = measured_peak()
-        local_vox = int(np.prod(plan.local_shape))
+        local_vox = int(np.prod(plan.local_shape)) if not peer else plan.owned_voxels
         ms_per_step = total_ms / args.steps
         ach = (BYTES_A + BYTES_B) * local_vox / (ms_per_step * 1e-3) / 1e9       # 96 B/voxel contract figure
         roofline = {"bound": "hbm",
@@ -94,30 +104,36 @@ def run_sharded(args):
             roofline["moved"] = {"bytes_per_voxel": 76, "GB/s": moved, "frac": moved / peak}
         # ---- end to end through the public sharded API with pinned host buffers ----------------------
         e2e = None
+        if peer:
+            sh.close()
         del sh
         torch.cuda.empty_cache()
         if not args.no_e2e:
             try:
                 iters = args.e2e_iters
-                host_in = tv.pinned_empty(plan.local_shape, np.float32)
-                host_out = tv.pinned_empty(plan.local_shape, np.float32)
+                host_in = tv.pinned_empty(tuple(x.shape), np.float32)
+                host_out = tv.pinned_empty(tuple(x.shape), np.float32)
                 torch.from_numpy(host_in).copy_(x)
                 del x
                 torch.cuda.empty_cache()
                 torch.cuda.synchronize()
                 dist.barrier()
                 t0 = time.perf_counter()
-                xd = torch.empty(plan.local_shape, dtype=torch.float32, device=dev)
+                xd = torch.empty(host_in.shape, dtype=torch.float32, device=dev)
                 xd.copy_(torch.from_numpy(host_in), non_blocking=True)
-                recon, bn, dl = sharded.denoise4D_sharded(xd, mu, iters, True, plan=plan, schedule=args.schedule)
+                if peer:
+                    recon, bn, dl = sharded.denoise4D_peer(xd, mu, iters, True, plan=plan)
+                else:
+                    recon, bn, dl = sharded.denoise4D_sharded(xd, mu, iters, True, plan=plan, schedule=args.schedule)
                 torch.from_numpy(host_out).copy_(recon, non_blocking=True)
                 torch.cuda.synchronize()
                 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-                nbytes = int(np.prod(plan.local_shape)) * 4
+                nbytes = int(np.prod(host_in.shape)) * 4
                 e2e = {"value": gvox * iters / float(dt[0]) / 1e9, "unit": UNIT,
                        "h2d_bytes_per_step": nbytes * world / iters, "d2h_bytes_per_step": nbytes * world / iters,
-                       "call": f"sharded.denoise4D_sharded(shard from pinned host, iterations={iters}, FISTA=True) on every rank",
+                       "call": f"sharded.{'denoise4D_peer' if peer else 'denoise4D_sharded'}(shard from pinned host, "
+                               f"iterations={iters}, FISTA=True) on every rank",
                        "wall_s": float(dt[0]), "delta_last": float(dl[-1])}
             except Exception as e:          # e.g. not enough pinned host memory on this box
                 e2e = {"value": None, "unit": UNIT, "error": repr(e)[:200]}

@@ -31,6 +31,10 @@ class StepOpts(C.Structure):
         ("flags", C.c_int32),
         ("l2_budget_bytes", C.c_int64),
         ("row_pitch", C.c_int64),
+        ("peer_lo_recon", C.c_void_p),
+        ("peer_hi_recon", C.c_void_p),
+        ("peer_hi_b0", C.c_void_p),
+        ("peer_hi_d0", C.c_void_p),
     ]
 
 
@@ -89,6 +93,9 @@ PROTOTYPES = {
     "cytvdn_set_device": (C.c_int, [C.c_int]),
     "cytvdn_get_device": (C.c_int, [C.POINTER(C.c_int)]),
     "cytvdn_mem_info": (C.c_int, [_i64p, _i64p]),
+    "cytvdn_ipc_get_handle": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
+    "cytvdn_ipc_open": (C.c_int, [C.POINTER(C.c_ubyte), _vpp]),
+    "cytvdn_ipc_close": (C.c_int, [_vp]),
     "cytvdn_launch_count": (C.c_int64, []),
 }
 

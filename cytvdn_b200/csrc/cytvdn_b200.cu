@@ -419,6 +419,7 @@ int run_sse(int64_t n, const void *a, const void *b, double *out, cudaStream_t s
 
 // ---- fused iteration ------------------------------------------------------------------------------
 struct FusedCall {
+    const void *lo_u, *hi_u, *hi_b0, *hi_d0;     // peer pointers (axis-0 halo on neighbouring GPUs) or NULL
     Dims D;
     const void *orig, *uin;
     void *uout;
@@ -439,7 +440,7 @@ int run_fused(const FusedCall &c)
 {
     FusedParams<T> P;
     memset(&P, 0, sizeof P);
-    uintptr_t pb = bits(c.orig) | bits(c.uin) | bits(c.uout);
+    uintptr_t pb = bits(c.orig) | bits(c.uin) | bits(c.uout) | bits(c.lo_u) | bits(c.hi_u) | bits(c.hi_b0) | bits(c.hi_d0);
     int nax = 0;
     for (int k = 0; k < 4; ++k) {
         if (c.D.ndim == 3 && k == 2) continue;
@@ -461,6 +462,7 @@ int run_fused(const FusedCall &c)
     if (int rc = make_sweep(c.D, vw, sizeof(T), c.opts, 2 * arrays, &P.S)) return rc;
     P.f = (const T *)c.orig; P.uin = (const T *)c.uin; P.uout = (T *)c.uout;
     P.tk = (T)c.tk; P.zero_wrap = c.zero_wrap;
+    P.lo_u = (const T *)c.lo_u; P.hi_u = (const T *)c.hi_u; P.hi_b0 = (const T *)c.hi_b0; P.hi_d0 = (const T *)c.hi_d0;
     Workspace ws;
     if (int rc = get_workspace(c.st, &ws)) return rc;
     P.W.partials = ws.partials; P.W.ticket = ws.ticket; P.W.out = c.sums_dev;
@@ -640,6 +642,11 @@ int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void
         if (opts && ((opts->zero_wrap_mask >> k) & 1)) c.zero_wrap |= 1 << s;
     }
     c.orig = orig; c.uin = recon_in; c.uout = recon_out;
+    if (opts) {
+        c.lo_u = opts->peer_lo_recon; c.hi_u = opts->peer_hi_recon; c.hi_b0 = opts->peer_hi_b0; c.hi_d0 = opts->peer_hi_d0;
+        if (c.hi_u && (!c.hi_b0 || (d_in && !c.hi_d0)))
+            return fail(CYTVDN_E_INVALID, "peer_hi_recon needs peer_hi_b0 (and peer_hi_d0 with FISTA)");
+    }
     c.fista = d_in != nullptr; c.tk = tk; c.sums_dev = sums_dev; c.opts = opts; c.st = (cudaStream_t)stream;
     return dtype == CYTVDN_F32 ? run_fused<float>(c) : run_fused<double>(c);
 }
@@ -993,6 +1000,28 @@ int cytvdn_memset(void *dst, int value, int64_t bytes, void *stream)
 int cytvdn_stream_synchronize(void *stream) { CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream)); return CYTVDN_OK; }
 int cytvdn_set_device(int device) { CUDA_TRY(cudaSetDevice(device)); return CYTVDN_OK; }
 int cytvdn_get_device(int *device) { if (!device) return fail(CYTVDN_E_INVALID, "NULL"); CUDA_TRY(cudaGetDevice(device)); return CYTVDN_OK; }
+int cytvdn_ipc_get_handle(void *ptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!ptr || !handle) return fail(CYTVDN_E_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    return CYTVDN_OK;
+}
+int cytvdn_ipc_open(const unsigned char handle[64], void **peer_ptr)
+{
+    if (!handle || !peer_ptr) return fail(CYTVDN_E_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CYTVDN_OK;
+}
+int cytvdn_ipc_close(void *peer_ptr)
+{
+    if (peer_ptr) CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return CYTVDN_OK;
+}
 int cytvdn_mem_info(int64_t *free_bytes, int64_t *total_bytes)
 {
     size_t f = 0, t = 0;

@@ -30,6 +30,13 @@ struct FusedParams {
     T tk;
     int32_t bc[4];        // 0 periodic, 2 Jia-Zhao (mirror is undefined for half-step B)
     int32_t zero_wrap;    // bit k: b'_k beyond the last index of axis k is 0 (sharded upper edge)
+    // Axis-0 halo read straight from the neighbouring GPUs' memory (peer pointers over NVLink; nullptr = none):
+    // the lower neighbour's LAST plane of recon stands for index -1, the upper neighbour's FIRST planes of
+    // recon / b_0 / d_0 for index n0.  Same in-plane layout (N1, N2, pitch) as the local arrays.
+    const T *lo_u;        // already offset to the start of that last plane
+    const T *hi_u;
+    const T *hi_b0;
+    const T *hi_d0;
     RedWork W;            // out[0] = sum|b'|, out[1] = sum|recon' - recon|, out[2] = sum|recon|
 };
 
@@ -83,6 +90,15 @@ tv_fused_kernel(const FusedParams<T> P)
             yoff[d] = at_end[d] ? e - span : e + stride[d];          // forward neighbour (wraps to index 0)
         }
 
+        // axis-0 neighbours that live on another GPU: same in-plane offset, other base pointer
+        const int64_t inplane = e - (int64_t)c.i * S.st0;
+        const bool lo_peer = c.i == 0 && P.lo_u != nullptr;
+        const bool hi_peer = at_end[0] && P.hi_u != nullptr;
+        const T *pv0_ptr = lo_peer ? P.lo_u + inplane : P.uin + poff[0];
+        const T *uy0_ptr = hi_peer ? P.hi_u + inplane : P.uin + yoff[0];
+        const T *by0_ptr = hi_peer ? P.hi_b0 + inplane : P.bin[0] + yoff[0];
+        const T *dy0_ptr = FISTA ? (hi_peer ? P.hi_d0 + inplane : P.din[0] + yoff[0]) : nullptr;
+
         // ---------------- phase 1: this thread's own voxels (first touch of every line: HBM) ----------
         const Vec<T, VW> us = ld_self(P.uin + e);
         const Vec<T, VW> f = ld_self(P.f + e);
@@ -108,10 +124,10 @@ tv_fused_kernel(const FusedParams<T> P)
         if (__syncthreads_or(left != left) == 0x5a5a5a5a) return;       // never taken (result is 0 or 1)
 #pragma unroll
         for (int d = 0; d < NFAR; ++d) {
-            pv[d] = ld_ro_ordered<T, VW>(P.uin + poff[d]);
-            uy[d] = ld_ro_ordered<T, VW>(P.uin + yoff[d]);
-            by[d] = ld_ro_ordered<T, VW>(P.bin[d] + yoff[d]);
-            if (FISTA) dy[d] = ld_ro_ordered<T, VW>(P.din[d] + yoff[d]);
+            pv[d] = ld_ro_ordered<T, VW>(d == 0 ? pv0_ptr : P.uin + poff[d]);
+            uy[d] = ld_ro_ordered<T, VW>(d == 0 ? uy0_ptr : P.uin + yoff[d]);
+            by[d] = ld_ro_ordered<T, VW>(d == 0 ? by0_ptr : P.bin[d] + yoff[d]);
+            if (FISTA) dy[d] = ld_ro_ordered<T, VW>(d == 0 ? dy0_ptr : P.din[d] + yoff[d]);
         }
         if (c.l0 == 0) left = (P.bc[3] == 2) ? us.v[0] : __ldg(P.uin + e + (S.n3 - 1));
         else if (lane == 0) left = __ldg(P.uin + e - 1);
@@ -159,8 +175,9 @@ tv_fused_kernel(const FusedParams<T> P)
 #pragma unroll
         for (int d = 0; d < NFAR; ++d) {
             Vec<T, VW> vs, ns;
-            const bool zero = at_end[d] && ((P.zero_wrap >> d) & 1);
-            const bool jz0 = at_end[d] && P.bc[d] == 2;      // neighbour sits at index 0: difference is 0
+            const bool peer_fwd = d == 0 && hi_peer;          // forward neighbour is a real plane of the next GPU
+            const bool zero = at_end[d] && ((P.zero_wrap >> d) & 1) && !peer_fwd;
+            const bool jz0 = at_end[d] && P.bc[d] == 2 && !peer_fwd;   // neighbour sits at index 0: difference is 0
 #pragma unroll
             for (int v = 0; v < VW; ++v) {
                 acc_update<T, FISTA>(us.v[v], pv[d].v[v], bs[d].v[v], FISTA ? ds[d].v[v] : T(0), P.clip[d], P.tk,

@@ -720,3 +720,247 @@ def emulate_on_one_device(gdata, mu, world, grid=None, iterations=10, FISTA=True
     g = tot.cpu().numpy()
     with np.errstate(all="ignore"):
         return out, g[:n, 0].copy(), (g[:n, 1] / g[:n, 2]).copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# "peer" schedule: no exchange step at all.  Every rank keeps ONLY its owned planes; the fused kernel reads
+# the axis-0 halo (the lower neighbour's last recon plane, the upper neighbour's first recon / b_0 / d_0 planes)
+# straight from the neighbours' HBM through CUDA-IPC peer pointers over NVLink.  One launch per iteration, one
+# tiny all-reduce as the inter-iteration barrier (a rank may not overwrite a state set its neighbours still read).
+# ------------------------------------------------------------------------------------------------
+class _DevArray:
+    """Lets torch view a raw device pointer (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerShard:
+    """Device state of one rank for the peer schedule: owned planes only, one cytvdn_malloc arena
+    (exportable through CUDA IPC), two state sets (the fused iteration is out of place)."""
+
+    def __init__(self, plan: ShardPlan, owned, mu, lam=None, fista=True, n_iter=1, group=None, connect=True):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.torch, self._lib, self.lib, self.dist, self.group = torch, _lib, _lib.load(), dist, group
+        _lib.require_gpu()
+        assert plan.grid[1] == 1, "the peer schedule splits scan axis 0 only"
+        assert owned.is_cuda and owned.is_contiguous() and owned.dtype in (torch.float32, torch.float64)
+        n_own = plan.valid[0][1] - plan.valid[0][0]
+        assert tuple(owned.shape) == (n_own,) + tuple(plan.gshape[1:]), (tuple(owned.shape), plan.gshape)
+        self.plan, self.fista, self.dev = plan, fista, owned.device
+        dt = np.float32 if owned.dtype == torch.float32 else np.float64
+        self.tdtype, elem = owned.dtype, (4 if dt == np.float32 else 8)
+        mu = np.asarray(mu, dtype=dt)
+        lam = (mu * 1.0 / 32.0) if lam is None else np.asarray(lam, dtype=dt)
+        self.clip = (C.c_double * 4)(*[float(v) for v in (1.0 / lam)])
+        self.w = (C.c_double * 4)(*[float(v) for v in (lam / mu).astype(dt)])
+        self.code = 0 if dt == np.float32 else 1
+        self.bc_mode = 0 if plan.periodic else 2
+        # rows padded to the 16-byte vector width (cytvdn_step_opts.row_pitch)
+        self.n3 = int(owned.shape[3])
+        vwf = 16 // elem
+        self.n3p = (self.n3 + vwf - 1) // vwf * vwf
+        self.shape_p = (n_own,) + tuple(plan.gshape[1:3]) + (self.n3p,)
+        self.plane_elems = int(plan.gshape[1]) * int(plan.gshape[2]) * self.n3p
+        numel = n_own * self.plane_elems
+        self.pitch = (numel * elem + 255) // 256 * 256                  # bytes between arrays in the arena
+        per = 1 + 4 * (2 if fista else 1)                               # recon, b x4 (, d x4)
+        self.n_arrays = 1 + 2 * per
+        self.arena = C.c_void_p()
+        _lib.check(self.lib.cytvdn_malloc(C.byref(self.arena), self.n_arrays * self.pitch))
+        self.sh = (C.c_int64 * 4)(n_own, *[int(v) for v in plan.gshape[1:]])
+        typestr = "<f4" if dt == np.float32 else "<f8"
+        view = lambda k: torch.as_tensor(_DevArray(self.arena.value + k * self.pitch, self.shape_p, typestr), device=self.dev)
+        # arena layout (identical on every rank): 0 orig | set s: 1 + s*per + (0 recon, 1..4 b, 5..8 d)
+        self.per = per
+        self.orig = view(0)
+        self.sets = [{"recon": view(1 + s * per), "b": [view(1 + s * per + 1 + k) for k in range(4)],
+                      "d": [view(1 + s * per + 5 + k) for k in range(4)] if fista else None} for s in range(2)]
+        self.orig.zero_()
+        self.orig[..., :self.n3].copy_(owned)
+        self.sets[0]["recon"].copy_(self.orig)
+        for s in range(2):
+            for t in self.sets[s]["b"] + (self.sets[s]["d"] or []):
+                t.zero_()
+        self.cur = 0
+        self.sums = torch.zeros((max(n_iter, 1), 4), dtype=torch.float64, device=self.dev)
+        self.token = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.launches = 0
+        self.peer_ptr, self.peer_info, self.local = {}, {}, False
+        if connect:
+            self.connect_ipc()
+
+    def connect_local(self, shards):
+        """All ranks live in THIS process (validation on one GPU): neighbours are plain pointers."""
+        self.local = True
+        for side, has in (("lo", self.plan.has_lo[0]), ("hi", self.plan.has_hi[0])):
+            if has:
+                r = self.plan.peer(0, -1 if side == "lo" else +1)
+                self.peer_ptr[r] = C.c_void_p(shards[r].arena.value)
+                self.peer_info[r] = (None, int(shards[r].sh[0]), shards[r].pitch)
+
+    def connect_ipc(self):
+        """Exchange CUDA-IPC handles of the arenas and map the neighbours' (one process per GPU)."""
+        torch, dist, plan, _lib, group = self.torch, self.dist, self.plan, self._lib, self.group
+        n_own = int(self.sh[0])
+        if plan.world > 1:
+            h = (C.c_ubyte * 64)()
+            _lib.check(self.lib.cytvdn_ipc_get_handle(self.arena, h))
+            info = [None] * plan.world
+            dist.all_gather_object(info, (bytes(h), n_own, self.pitch), group=group)
+            self.peer_info = info
+            for side, has in (("lo", plan.has_lo[0]), ("hi", plan.has_hi[0])):
+                if not has:
+                    continue
+                r = plan.peer(0, -1 if side == "lo" else +1)
+                if r not in self.peer_ptr:
+                    q = C.c_void_p()
+                    ph = (C.c_ubyte * 64)(*info[r][0])
+                    _lib.check(self.lib.cytvdn_ipc_open(ph, C.byref(q)))
+                    self.peer_ptr[r] = q
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=group)          # everybody's initial state is in place before anyone reads it
+
+    def _array_ptr(self, base, pitch, s, which, k=0):
+        idx = 1 + s * self.per + {"recon": 0, "b": 1 + k, "d": 5 + k}[which]
+        return base + idx * pitch
+
+    def step(self, it, tk_ratio, fista):
+        """One fused iteration over the owned planes, halo read from the neighbours, then the barrier."""
+        torch, plan = self.torch, self.plan
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        s, elem = self.cur, (4 if self.code == 0 else 8)
+        src, dst = self.sets[s], self.sets[1 - s]
+        o = self._lib.StepOpts()
+        o.row_pitch = self.n3p
+        o.flags = plan.jz_flags
+        if plan.has_lo[0]:
+            r = plan.peer(0, -1)
+            n_r, pitch_r = self.peer_info[r][1], self.peer_info[r][2]
+            o.peer_lo_recon = self._array_ptr(self.peer_ptr[r].value, pitch_r, s, "recon") + (n_r - 1) * self.plane_elems * elem
+        if plan.has_hi[0]:
+            r = plan.peer(0, +1)
+            pitch_r = self.peer_info[r][2]
+            o.peer_hi_recon = self._array_ptr(self.peer_ptr[r].value, pitch_r, s, "recon")
+            o.peer_hi_b0 = self._array_ptr(self.peer_ptr[r].value, pitch_r, s, "b", 0)
+            if fista:
+                o.peer_hi_d0 = self._array_ptr(self.peer_ptr[r].value, pitch_r, s, "d", 0)
+        elif plan.has_lo[0]:
+            o.zero_wrap_mask = 1               # global upper edge: nothing beyond the last plane (Jia-Zhao)
+        ptrs = lambda ts: (C.c_void_p * 4)(*[t.data_ptr() for t in ts])
+        self._lib.check(self.lib.cytvdn_fused_iteration(
+            4, self.sh, self.code, self.orig.data_ptr(), src["recon"].data_ptr(), dst["recon"].data_ptr(),
+            ptrs(src["b"]), ptrs(dst["b"]), ptrs(src["d"]) if fista else None, ptrs(dst["d"]) if fista else None,
+            float(tk_ratio), self.clip, self.w, self.bc_mode, self.sums[it].data_ptr(), C.byref(o), st))
+        self.launches += 1
+        self.cur = 1 - s
+        if plan.world > 1 and not self.local:  # nobody starts the next iteration before everybody finished this one
+            self.dist.all_reduce(self.token, group=self.group)
+
+    def result(self):
+        r = self.sets[self.cur]["recon"]
+        return r if self.n3p == self.n3 else r[..., :self.n3]
+
+    def close(self):
+        if not self.local:
+            for q in self.peer_ptr.values():
+                self.lib.cytvdn_ipc_close(q)
+        self.peer_ptr = {}
+        if self.arena:
+            self.torch.cuda.synchronize(self.dev)
+            if self.plan.world > 1 and not self.local:
+                self.dist.barrier(group=self.group)      # neighbours have unmapped it
+            self.lib.cytvdn_free(self.arena)
+            self.arena = None
+
+
+def denoise4D_peer(owned, mu, iterations=10, FISTA=True, stopping_relative_change=None, *, plan: ShardPlan, group=None,
+                   lam=None):
+    """Sharded ``denoise4D`` with the peer schedule.  ``owned``: this rank's OWNED planes only
+    (``global[plan.owned_global]``, contiguous CUDA tensor; 1-D split).  Returns ``(recon_owned, b_norm, delta)``."""
+    import torch
+    import torch.distributed as dist
+    unaccelerated = not FISTA
+    if type(iterations) in (list, tuple):
+        FISTA, unaccelerated = True, True
+        nF, nU = int(iterations[0]), int(iterations[1])
+    else:
+        nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
+    n, world = nF + nU, plan.world
+    sh = PeerShard(plan, owned, mu, lam, fista=nF > 0, n_iter=n, group=group)
+    try:
+        ran = np.zeros(n, dtype=bool)
+        glob = torch.zeros((max(n, 1), 4), dtype=torch.float64, device=owned.device)
+        tk = 1.0
+        for phase, count in ((0, nF), (1, nU)):
+            for j in range(count):
+                it = j if phase == 0 else nF + j
+                tkr = 0.0
+                if phase == 0:
+                    tkr, tk = fista_ratio(tk)
+                sh.step(it, tkr, phase == 0)
+                ran[it] = True
+                if stopping_relative_change is not None:
+                    s = sh.sums[it].clone()
+                    if world > 1:
+                        dist.all_reduce(s, group=group)
+                    glob[it] = s
+                    dl = float(s[1] / s[2])
+                    if owned.dtype == torch.float32:
+                        dl = float(np.float32(dl))
+                    if dl < stopping_relative_change:
+                        break
+        if stopping_relative_change is None and n > 0:
+            glob = sh.sums.clone()
+            if world > 1:
+                dist.all_reduce(glob, group=group)
+        g = glob.cpu().numpy()
+        dt = np.float32 if owned.dtype == torch.float32 else np.float64
+        with np.errstate(all="ignore"):
+            b_norm = np.where(ran, g[:n, 0], 0.0).astype(dt)
+            delta = np.where(ran, g[:n, 1] / g[:n, 2], 0.0).astype(dt)
+        out = sh.result().clone()
+        torch.cuda.current_stream(owned.device).synchronize()
+        return out, b_norm, delta
+    finally:
+        sh.close()
+
+
+def emulate_peer_on_one_device(gdata, mu, world, iterations=10, FISTA=True, periodic=False, lam=None):
+    """All ranks of the peer schedule on ONE device (neighbours are plain pointers, launches in lockstep on one
+    stream).  Returns (assembled recon, b_norm, delta)."""
+    import torch
+    if type(iterations) in (list, tuple):
+        nF, nU = int(iterations[0]), int(iterations[1])
+    else:
+        nF, nU = int(iterations * FISTA), int(iterations * (not FISTA))
+    n = nF + nU
+    plans = [ShardPlan(gdata.shape, world, r, None, periodic) for r in range(world)]
+    shards = [PeerShard(p, gdata[p.owned_global].contiguous(), mu, lam, fista=nF > 0, n_iter=n, connect=False)
+              for p in plans]
+    try:
+        for s in shards:
+            s.connect_local(shards)
+        tk = 1.0
+        for phase, cnt in ((0, nF), (1, nU)):
+            for j in range(cnt):
+                it = j if phase == 0 else nF + j
+                tkr = 0.0
+                if phase == 0:
+                    tkr, tk = fista_ratio(tk)
+                for s in shards:
+                    s.step(it, tkr, phase == 0)
+        out = torch.empty_like(gdata)
+        tot = torch.zeros((max(n, 1), 4), dtype=torch.float64, device=gdata.device)
+        for s in shards:
+            out[s.plan.owned_global] = s.result()
+            tot += s.sums
+        g = tot.cpu().numpy()
+        with np.errstate(all="ignore"):
+            return out, g[:n, 0].copy(), (g[:n, 1] / g[:n, 2]).copy()
+    finally:
+        for s in shards:
+            s.close()

@@ -82,6 +82,14 @@ typedef struct cytvdn_step_opts {
     int32_t flags;              /* bit 0: dynamic tile scheduling, bits 8..11: per-axis Jia-Zhao (see below) */
     int64_t l2_budget_bytes;
     int64_t row_pitch;          /* elements between consecutive rows of the fast axis; 0 = dense (= extent) */
+    /* cytvdn_fused_iteration only: axis-0 halo read from neighbouring GPUs through peer pointers
+       (cytvdn_ipc_open); NULL = no neighbour on that side.  peer_lo_recon points at the START OF THE LAST
+       PLANE of the lower neighbour's recon_in; the peer_hi_* point at the upper neighbour's recon_in / b_in[0] /
+       d_in[0] (their first plane is used).  Same inner shape and row pitch as the local arrays. */
+    const void *peer_lo_recon;
+    const void *peer_hi_recon;
+    const void *peer_hi_b0;
+    const void *peer_hi_d0;
 } cytvdn_step_opts;
 
 /*
@@ -218,6 +226,15 @@ int cytvdn_stream_synchronize(void *stream);
 int cytvdn_set_device(int device);
 int cytvdn_get_device(int *device);
 int cytvdn_mem_info(int64_t *free_bytes, int64_t *total_bytes);
+/*
+ * Peer access to another process's device allocation on the same node (one process per GPU): the owner
+ * exports a 64-byte handle of an allocation made with cytvdn_malloc, the peer opens it and gets a pointer that
+ * kernels on ITS device can dereference over NVLink.  Used by the sharded path to read halo planes straight
+ * from the neighbour's HBM inside the fused sweep (no exchange step).
+ */
+int cytvdn_ipc_get_handle(void *ptr, unsigned char handle[64]);
+int cytvdn_ipc_open(const unsigned char handle[64], void **peer_ptr);
+int cytvdn_ipc_close(void *peer_ptr);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t cytvdn_launch_count(void);
 

@@ -804,3 +804,21 @@ def test_fused_schedule_is_faster_than_two_pass(tv):
         tv.denoise4D(x, mu, 12, True, quiet=True, schedule=sched, timing=tm)
         t[sched] = min(t.get(sched, 1e30), tm["loop_ms"])
     assert t["fused"] < 0.93 * t["two_pass"], t
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+@pytest.mark.parametrize("iters", [11, [4, 3]])
+def test_peer_schedule_equals_single_gpu(tv, world, periodic, iters):
+    """Peer schedule: owned planes only, axis-0 halo read through pointers into the neighbours' arenas (here all
+    ranks live in one process, so the pointers are local; tools/check_sharded_nccl.py runs it with CUDA IPC)."""
+    import torch
+    from cytvdn_b200 import sharded
+    rng = np.random.default_rng(400 + world)
+    data = counts(rng, (13, 6, 8, 14), "float32")          # uneven split, rows padded to 16
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = tv.denoise4D(data, mu, iters, True, BC_mode=0 if periodic else 2, quiet=True, schedule="two_pass")
+    got, bn, dl = sharded.emulate_peer_on_one_device(torch.from_numpy(data).cuda(), mu, world, iters, True, periodic)
+    assert np.array_equal(got.cpu().numpy(), ref[0])
+    np.testing.assert_allclose(bn, ref[1].astype(np.float64), rtol=1e-5)
+    np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)

@@ -36,7 +36,7 @@ def main():
         grids = [None] + ([(2, world // 2)] if world % 2 == 0 and world >= 4 else [])
         for periodic in (False, True):
             for grid in grids:
-                for sched in ("fused", "two_pass"):
+                for sched in ("fused", "two_pass") + (("peer",) if grid is None else ()):
                     for iters, stop in ((25, None), ([8, 5], None), (60, 0.002)):
                         cases.append((grid, sched, iters, stop, periodic))
         for grid, sched, iters, stop, periodic in cases:
@@ -44,10 +44,14 @@ def main():
             plan = sharded.ShardPlan(gshape, world, rank, grid, periodic)
             whole = synth.stem4d_device(gshape, seed=11, counts=400.0, device=dev)
             shard = plan.extract(whole).contiguous()
-            recon, bn, dl = sharded.denoise4D_sharded(shard, mu, iters, True, stop, plan=plan, schedule=sched)
-            # gather the owned blocks on rank 0
             out = torch.zeros(gshape, dtype=torch.float32, device=dev)
-            out[plan.owned_global] = recon[plan.owned_local]
+            if sched == "peer":       # owned planes only, halo read from the neighbours' HBM through CUDA IPC
+                recon, bn, dl = sharded.denoise4D_peer(whole[plan.owned_global].contiguous(), mu, iters, True, stop,
+                                                       plan=plan)
+                out[plan.owned_global] = recon
+            else:
+                recon, bn, dl = sharded.denoise4D_sharded(shard, mu, iters, True, stop, plan=plan, schedule=sched)
+                out[plan.owned_global] = recon[plan.owned_local]     # gather the owned blocks on rank 0
             dist.all_reduce(out)                            # blocks are disjoint: the sum is the assembly
             if rank == 0:
                 ref = tv.denoise4D(whole, mu, iters, True, stop, BC_mode=0 if periodic else 2, quiet=True,
