@@ -498,8 +498,13 @@ int run_fused(const FusedCall &c)
                 k<<<grid, kBlock, 0, c.st>>>(P);
                 return CYTVDN_OK;
             };
-            if (c.fista) return ax2 ? go(tv_fused_kernel<T, VW, true, true>) : go(tv_fused_kernel<T, VW, true, false>);
-            return ax2 ? go(tv_fused_kernel<T, VW, false, true>) : go(tv_fused_kernel<T, VW, false, false>);
+            auto pick = [&](auto PEERc) -> int {
+                constexpr bool PEER = decltype(PEERc)::value;
+                if (c.fista) return ax2 ? go(tv_fused_kernel<T, VW, true, true, PEER>) : go(tv_fused_kernel<T, VW, true, false, PEER>);
+                return ax2 ? go(tv_fused_kernel<T, VW, false, true, PEER>) : go(tv_fused_kernel<T, VW, false, false, PEER>);
+            };
+            const bool peer = c.lo_u || c.hi_u;
+            return peer ? pick(std::true_type{}) : pick(std::false_type{});
         }))
         return rc;
     g_launches.fetch_add(1, std::memory_order_relaxed);

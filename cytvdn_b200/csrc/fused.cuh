@@ -48,7 +48,9 @@ __device__ __forceinline__ void acc_update(T u, T p, T b, T d, T clip, T tk, T &
     bn = FISTA ? (v + tk * (v - d)) : v;
 }
 
-template <typename T, int VW, bool FISTA, bool AX2>
+// PEER: axis-0 halo planes may live on a neighbouring GPU (pointer selects; costs ~2 % when compiled in, so the
+// single-GPU / NCCL schedules use the PEER=false instantiation)
+template <typename T, int VW, bool FISTA, bool AX2, bool PEER>
 #ifndef FUSED_MINB
 #define FUSED_MINB 2
 #endif
@@ -92,8 +94,8 @@ tv_fused_kernel(const FusedParams<T> P)
 
         // axis-0 neighbours that live on another GPU: same in-plane offset, other base pointer
         const int64_t inplane = e - (int64_t)c.i * S.st0;
-        const bool lo_peer = c.i == 0 && P.lo_u != nullptr;
-        const bool hi_peer = at_end[0] && P.hi_u != nullptr;
+const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
+        const bool hi_peer = PEER && at_end[0] && P.hi_u != nullptr;
         const T *pv0_ptr = lo_peer ? P.lo_u + inplane : P.uin + poff[0];
         const T *uy0_ptr = hi_peer ? P.hi_u + inplane : P.uin + yoff[0];
         const T *by0_ptr = hi_peer ? P.hi_b0 + inplane : P.bin[0] + yoff[0];
