@@ -343,7 +343,7 @@ def run_single(args):
         e2e = {"value": vox * iters / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes / iters,
                "d2h_bytes_per_step": nbytes / iters,
                "call": f"tv.denoise4D(pinned host fp32, iterations={iters}, FISTA=True, schedule={tm.get('schedule')})",
-               "wall_s": dt, "setup_ms": tm.get("setup_ms"), "loop_ms": tm.get("loop_ms"), "finish_ms": tm.get("finish_ms"),
+               "wall_s": dt, "pcie_pipeline_boxes": tm.get("pipeline_boxes"), "setup_ms": tm.get("setup_ms"), "loop_ms": tm.get("loop_ms"), "finish_ms": tm.get("finish_ms"),
                "h2d_bytes_total": nbytes, "d2h_bytes_total": nbytes}
     cpu = None
     if not args.no_cpu:

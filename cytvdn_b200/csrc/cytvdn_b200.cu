@@ -8,6 +8,7 @@
 #include "fused_tma.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -791,6 +792,13 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     Dims D;
     if (int rc = validate_params(p, &D)) return rc;
     if (!data || !recon) return fail(CYTVDN_E_INVALID, "data / recon is NULL");
+    // CYTVDN_TRACE=1: host-clock milestones of the call on stderr (where the wall time outside the CUDA events goes)
+    const bool trace = [] { const char *e = getenv("CYTVDN_TRACE"); return e && *e && strcmp(e, "0"); }();
+    const auto t_start = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (trace) fprintf(stderr, "[cytvdn_denoise] %8.2f ms  %s\n",
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what);
+    };
     if (data == recon) return fail(CYTVDN_E_INVALID, "recon must not alias data (the input is read in every iteration)");
     const int nF = p->iters_fista, nU = p->iters_plain, nIt = nF + nU;
     if (nIt > 0 && (!bnorm || !delta)) return fail(CYTVDN_E_INVALID, "bnorm / delta is NULL");
@@ -816,7 +824,11 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     int prev_dev = -1;
     CUDA_TRY(cudaGetDevice(&prev_dev));
     if (!data_dev && p->device >= 0) CUDA_TRY(cudaSetDevice(p->device));
-    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+    struct Restore {
+        int d;
+        void now() { int c = -1; if (d >= 0 && (cudaGetDevice(&c) != cudaSuccess || c != d)) cudaSetDevice(d); d = -1; }
+        ~Restore() { now(); }
+    } restore{prev_dev};
     cudaStream_t st = (cudaStream_t)p->stream;
 
     // ---- schedule: fused single pass when it applies and the second state set fits ----------------
@@ -833,43 +845,122 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         }
     }
 
+    // ---- pipelining over PCIe (host arrays only) ----------------------------------------------------
+    // The array is cut into `nbox` boxes of axis-0 planes.  The first and the last `depth` iterations run box by
+    // box in wavefront order (box c may be at most one iteration ahead of box c+1, which is all the stencil's
+    // dependence cone asks for): box c starts iterating as soon as boxes c and c+1 have arrived, and is copied
+    // back as soon as ITS last iteration is done while the boxes behind it still iterate.  One host->device copy
+    // costs ~6.7 iterations (4 B/voxel at ~55 GB/s against 76 B/voxel at ~7 TB/s), so 16 boxes hide it.
+    // Needs the Jia-Zhao boundary (under the periodic one box 0 depends on the last box), fixed iteration
+    // counts (no stopping test, no per-iteration MSE: both need the whole array at one iteration).
+    // The last box takes its wrap term as 0 (zero_wrap): plane 0 of b_0 is identically 0 under Jia-Zhao.
+    int nbox = 1;
+    {
+        const bool can = fused && p->bc_mode == 2 && !p->use_stopping && !reference_data && nIt > 0 &&
+                         (!data_dev || !recon_dev);
+        int want = nb >= ((size_t)256 << 20) ? 16 : 1;
+        const char *env = getenv("CYTVDN_PIPELINE");
+        if (env && *env) want = atoi(env);
+        if (can && want > 1) nbox = (int)std::min<int64_t>(want, D.n[0] / 2);       // at least two planes per box
+        if (nbox < 2) nbox = 1;
+    }
+    const bool pipe = nbox > 1;
+    auto box_lo = [&](int c) -> int64_t { return D.n[0] * c / nbox; };
+    const int64_t plane_rows = D.n[1] * D.n[2];
+
     cudaEvent_t ev[4];
     for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
-    struct EvFree { cudaEvent_t *e; ~EvFree() { for (int k = 0; k < 4; ++k) cudaEventDestroy(e[k]); } } evfree{ev};
+    struct EvFree {
+        cudaEvent_t *e;
+        void now() { if (e) for (int k = 0; k < 4; ++k) cudaEventDestroy(e[k]); e = nullptr; }
+        ~EvFree() { now(); }
+    } evfree{ev};
     CUDA_TRY(cudaEventRecord(ev[0], st));
-
-    const size_t nsums = (size_t)(nIt + 1) * 4;
-    Arena pool;
-    {
-        const int64_t arrays = arrays_needed(p, fused, data_dev, recon_dev, reference_data && !ref_dev);
-        if (int rc = pool.reserve((size_t)arrays * Arena::padded(nb) + Arena::padded(nsums * sizeof(double)) + 4096))
-            return rc;
+    mark("entry checks done");
+    struct Side {                                   // copy stream + per-box events of the pipelined path
+        cudaStream_t s = nullptr;
+        std::vector<cudaEvent_t> up, down;
+        void now()
+        {
+            for (auto e : up) cudaEventDestroy(e);
+            for (auto e : down) cudaEventDestroy(e);
+            if (s) cudaStreamDestroy(s);
+            up.clear(); down.clear(); s = nullptr;
+        }
+        ~Side() { now(); }
+    } side;
+    if (pipe) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamWaitEvent(side.s, ev[0], 0));
+        auto mk = [&](std::vector<cudaEvent_t> &v) -> int {
+            v.reserve(nbox);
+            for (int c = 0; c < nbox; ++c) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); v.push_back(e); }
+            return CYTVDN_OK;
+        };
+        if (!data_dev) if (int rc = mk(side.up)) return rc;
+        if (!recon_dev) if (int rc = mk(side.down)) return rc;
     }
+
+    const size_t nsums = (size_t)(nIt + 1) * 4 * (size_t)nbox;
     void *b[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, *d[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     void *orig_d = nullptr, *rbuf[2] = {nullptr, nullptr}, *ref_d = nullptr;
     double *sums_d = nullptr;
-    // dense caller array -> internal array (any direction the pointers imply; pads zeroed)
-    auto copy_in = [&](void *dst, const void *src) -> int {
-        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDefault, st)); return CYTVDN_OK; }
-        CUDA_TRY(cudaMemsetAsync(dst, 0, nb, st));
-        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)n3p * elem, src, (size_t)n3 * elem, (size_t)n3 * elem, (size_t)rows,
-                                   cudaMemcpyDefault, st));
+    // dense caller array -> internal array, rows [r0, r0 + nr) (any direction the pointers imply; pads zeroed)
+    auto copy_in = [&](void *dst, const void *src, int64_t r0, int64_t nr, cudaStream_t s) -> int {
+        char *dp = (char *)dst + (size_t)r0 * n3p * elem;
+        const char *sp = (const char *)src + (size_t)r0 * n3 * elem;
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)nr * n3 * elem, cudaMemcpyDefault, s)); return CYTVDN_OK; }
+        CUDA_TRY(cudaMemsetAsync(dp, 0, (size_t)nr * n3p * elem, s));
+        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3p * elem, sp, (size_t)n3 * elem, (size_t)n3 * elem, (size_t)nr,
+                                   cudaMemcpyDefault, s));
         return CYTVDN_OK;
     };
-    auto copy_out = [&](void *dst, const void *src) -> int {
-        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDefault, st)); return CYTVDN_OK; }
-        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)n3 * elem, src, (size_t)n3p * elem, (size_t)n3 * elem, (size_t)rows,
-                                   cudaMemcpyDefault, st));
+    auto copy_out = [&](void *dst, const void *src, int64_t r0, int64_t nr, cudaStream_t s) -> int {
+        char *dp = (char *)dst + (size_t)r0 * n3 * elem;
+        const char *sp = (const char *)src + (size_t)r0 * n3p * elem;
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)nr * n3 * elem, cudaMemcpyDefault, s)); return CYTVDN_OK; }
+        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3 * elem, sp, (size_t)n3p * elem, (size_t)n3 * elem, (size_t)nr,
+                                   cudaMemcpyDefault, s));
         return CYTVDN_OK;
     };
+    auto upload_box = [&](int c) -> int {
+        const int64_t r0 = box_lo(c) * plane_rows, r1 = box_lo(c + 1) * plane_rows;
+        if (int rc = copy_in(orig_d, data, r0, r1 - r0, side.s)) return rc;
+        CUDA_TRY(cudaEventRecord(side.up[c], side.s));
+        return CYTVDN_OK;
+    };
+    // pinned (or registered) host memory: asynchronous copies, all enqueued up front; pageable memory: a copy
+    // blocks the host while it is staged, so the boxes are interleaved with the kernel launches instead
+    auto host_async = [&](const void *q) -> bool {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    };
+    int uploaded = 0;                                // boxes whose upload has been enqueued
+
+    // The input gets its own allocation so that its upload can start before (and run while) the big arena of
+    // the state arrays is being allocated (~30 ms for 80 GB).
+    Arena pool0, pool;
     if (data_dev) orig_d = const_cast<void *>(data);
-    else { if (int rc = pool.alloc(&orig_d, nb)) return rc; if (int rc = copy_in(orig_d, data)) return rc; }
+    else {
+        if (int rc = pool0.reserve(Arena::padded(nb))) return rc;
+        if (int rc = pool0.alloc(&orig_d, nb)) return rc;
+        if (!pipe) { if (int rc = copy_in(orig_d, data, 0, rows, st)) return rc; }
+        else if (host_async(data)) { for (; uploaded < nbox; ++uploaded) if (int rc = upload_box(uploaded)) return rc; }
+    }
+    mark("input allocated, upload enqueued");
+    {
+        const int64_t arrays = arrays_needed(p, fused, true, recon_dev, reference_data && !ref_dev);
+        if (int rc = pool.reserve((size_t)arrays * Arena::padded(nb) + Arena::padded(nsums * sizeof(double)) + 4096))
+            return rc;
+    }
+    mark("state arena allocated");
     if (recon_dev) rbuf[0] = recon;
     else if (int rc = pool.alloc(&rbuf[0], nb)) return rc;
     if (fused) if (int rc = pool.alloc(&rbuf[1], nb)) return rc;
     if (reference_data) {
         if (ref_dev) ref_d = const_cast<void *>(reference_data);
-        else { if (int rc = pool.alloc(&ref_d, nb)) return rc; if (int rc = copy_in(ref_d, reference_data)) return rc; }
+        else { if (int rc = pool.alloc(&ref_d, nb)) return rc; if (int rc = copy_in(ref_d, reference_data, 0, rows, st)) return rc; }
     }
     for (int k = 0; k < nd && nIt > 0; ++k) {
         for (int s = 0; s < (fused ? 2 : 1); ++s) {
@@ -879,20 +970,20 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         CUDA_TRY(cudaMemsetAsync(b[0][k], 0, nb, st));            // only the set that is read first
         if (nF > 0) CUDA_TRY(cudaMemsetAsync(d[0][k], 0, nb, st));
     }
-    // per iteration: [0] sum|b|, [1] sum|delta|, [2] sum|old|, [3] sse ; slot nIt holds MSE[0]
+    // per iteration (and box): [0] sum|b|, [1] sum|delta|, [2] sum|old|, [3] sse ; slot nIt holds MSE[0]
     if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
     CUDA_TRY(cudaMemsetAsync(sums_d, 0, nsums * sizeof(double), st));
     std::vector<double> sums_h(nsums, 0.0);
     double *pinned = nullptr;
     if (p->use_stopping) CUDA_TRY(cudaMallocHost(&pinned, 4 * sizeof(double)));
-    struct PinFree { double *p; ~PinFree() { if (p) cudaFreeHost(p); } } pinfree{pinned};
+    struct PinFree { double *p; void now() { if (p) cudaFreeHost(p); p = nullptr; } ~PinFree() { now(); } } pinfree{pinned};
 
     auto sse = [&](const void *a, const void *b, double *out) -> int {
         return p->dtype == CYTVDN_F32 ? run_sse<float>(nvox, a, b, out, st, n3, n3p)
                                       : run_sse<double>(nvox, a, b, out, st, n3, n3p);
     };
     if (reference_data)
-        if (int rc = sse(orig_d, ref_d, sums_d + (size_t)nIt * 4 + 3)) return rc;
+        if (int rc = sse(orig_d, ref_d, sums_d + (size_t)nIt * 4 * nbox + 3)) return rc;
 
     CUDA_TRY(cudaEventRecord(ev[1], st));
     // iteration 0 reads the reconstruction straight from the input (recon = datacube.copy(),
@@ -903,6 +994,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     double tk = 1.0;
     int done[2] = {0, 0};
     std::vector<char> ran(nIt > 0 ? nIt : 1, 0);
+    if (!pipe) {
     for (int phase = 0; phase < 2; ++phase) {
         const int n = phase == 0 ? nF : nU;
         for (int it = 0; it < n; ++it) {
@@ -945,29 +1037,104 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
             }
         }
     }
-    if (u_cur != rbuf[0])                      // zero iterations, or the fused ping-pong ended in the spare buffer
+    } else {
+        // ---- pipelined: wavefront over (box, iteration) at both ends, whole-array sweeps in between ----------
+        std::vector<double> tkr(nIt, 0.0);
+        for (int i = 0; i < nF; ++i) {                          // cyTVDN.py:154-156
+            const double tk_new = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
+            tkr[i] = (tk - 1.0) / tk_new;
+            tk = tk_new;
+        }
+        // iteration m reads state set m%2 and recon buffer (m-1)%2 (the input for m = 0), writes set (m+1)%2 and
+        // recon buffer m%2
+        auto iterate = [&](int m, int c) -> int {               // c < 0: the whole array
+            cytvdn_step_opts o = sopts;
+            if (c >= 0) {
+                o.box_lo[0] = box_lo(c); o.box_hi[0] = box_lo(c + 1);
+                if (c == nbox - 1) o.zero_wrap_mask |= 1;
+            }
+            const bool fi = m < nF;
+            const int in = m & 1, out = in ^ 1;
+            return cytvdn_fused_iteration(nd, p->shape, p->dtype, orig_d, m == 0 ? orig_d : rbuf[(m - 1) & 1], rbuf[m & 1],
+                                          b[in], b[out], fi ? d[in] : nullptr, fi ? d[out] : nullptr, tkr[m], p->clip,
+                                          p->lambda_mu, p->bc_mode, sums_d + ((size_t)m * nbox + (c < 0 ? 0 : c)) * 4, &o, st);
+        };
+        // iterations [m0, m1) of every box; within a step t = box + (iteration - m0) the higher boxes go first,
+        // so that box c+1 has finished iteration m-1 before box c starts iteration m
+        auto wave = [&](int m0, int m1, bool first, bool last) -> int {
+            const int depth = m1 - m0;
+            for (int t = 0; t < nbox + depth - 1; ++t) {
+                for (int c = std::min(t, nbox - 1); c >= 0 && t - c < depth; --c) {
+                    const int m = m0 + (t - c);
+                    if (first && m == 0 && !data_dev) {         // needs the planes of boxes c and c+1
+                        const int need = std::min(c + 1, nbox - 1);
+                        for (; uploaded <= need; ++uploaded) if (int rc = upload_box(uploaded)) return rc;
+                        CUDA_TRY(cudaStreamWaitEvent(st, side.up[need], 0));
+                    }
+                    if (int rc = iterate(m, c)) return rc;
+                    if (last && m == nIt - 1 && !recon_dev) CUDA_TRY(cudaEventRecord(side.down[c], st));
+                }
+            }
+            return CYTVDN_OK;
+        };
+        const int depth = nbox;
+        if (nIt <= 2 * depth + 2) {
+            if (int rc = wave(0, nIt, true, true)) return rc;
+        } else {
+            if (int rc = wave(0, depth, true, false)) return rc;
+            for (int m = depth; m < nIt - depth; ++m) if (int rc = iterate(m, -1)) return rc;
+            if (int rc = wave(nIt - depth, nIt, false, true)) return rc;
+        }
+        for (int i = 0; i < nIt; ++i) ran[i] = 1;
+        done[0] = nF; done[1] = nU;
+        u_cur = rbuf[(nIt - 1) & 1];
+        if (!recon_dev) {                                       // boxes go home as they finish
+            for (int c = 0; c < nbox; ++c) {
+                CUDA_TRY(cudaStreamWaitEvent(side.s, side.down[c], 0));
+                const int64_t r0 = box_lo(c) * plane_rows, r1 = box_lo(c + 1) * plane_rows;
+                if (int rc = copy_out(recon, u_cur, r0, r1 - r0, side.s)) return rc;
+            }
+            CUDA_TRY(cudaEventRecord(side.down[0], side.s));     // reuse: "all copies done"
+            CUDA_TRY(cudaStreamWaitEvent(st, side.down[0], 0));
+        }
+    }
+    if (recon_dev && u_cur != rbuf[0])         // zero iterations, or the fused ping-pong ended in the spare buffer
         CUDA_TRY(cudaMemcpyAsync(rbuf[0], u_cur, nb, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaEventRecord(ev[2], st));
+    mark("iterations enqueued");
 
-    if (!recon_dev) if (int rc = copy_out(recon, rbuf[0])) return rc;
+    if (!recon_dev && !pipe) if (int rc = copy_out(recon, u_cur, 0, rows, st)) return rc;
     CUDA_TRY(cudaMemcpyAsync(sums_h.data(), sums_d, nsums * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    mark("device work complete");
     for (int i = 0; i < nIt; ++i) {
-        bnorm[i] = ran[i] ? sums_h[(size_t)i * 4 + 0] : 0.0;
-        delta[i] = ran[i] ? sums_h[(size_t)i * 4 + 1] / sums_h[(size_t)i * 4 + 2] : 0.0;
-        if (mse) mse[i + 1] = ran[i] ? sums_h[(size_t)i * 4 + 3] : 0.0;
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = 0; c < nbox; ++c)                          // fixed order: deterministic
+            for (int q = 0; q < 4; ++q) s4[q] += sums_h[((size_t)i * nbox + c) * 4 + q];
+        bnorm[i] = ran[i] ? s4[0] : 0.0;
+        delta[i] = ran[i] ? s4[1] / s4[2] : 0.0;
+        if (mse) mse[i + 1] = ran[i] ? s4[3] : 0.0;
     }
-    if (mse) mse[0] = sums_h[(size_t)nIt * 4 + 3];
-    if (iters_done) { iters_done[0] = done[0]; iters_done[1] = done[1]; iters_done[2] = fused ? 2 : 1; }
+    if (mse) mse[0] = sums_h[(size_t)nIt * 4 * nbox + 3];
+    if (iters_done) { iters_done[0] = done[0]; iters_done[1] = done[1]; iters_done[2] = (fused ? 2 : 1) | (pipe ? nbox << 8 : 0); }
     CUDA_TRY(cudaEventRecord(ev[3], st));
     CUDA_TRY(cudaEventSynchronize(ev[3]));
-    pool.release();
     if (timing_ms) {
         float t = 0;
         CUDA_TRY(cudaEventElapsedTime(&t, ev[0], ev[1])); timing_ms[0] = t;
         CUDA_TRY(cudaEventElapsedTime(&t, ev[1], ev[2])); timing_ms[1] = t;
         CUDA_TRY(cudaEventElapsedTime(&t, ev[2], ev[3])); timing_ms[2] = t;
     }
+    side.now();
+    evfree.now();
+    pinfree.now();
+    restore.now();
+    mark("results delivered");
+    // cudaFree of the ~80 GB arena: 25-40 ms, now and then several hundred (tools/e2e_trace.py).  Handing it to a
+    // helper thread was tried and bought nothing: the caller's next allocations stall for as long as the free runs.
+    pool.release();
+    pool0.release();
+    mark("arenas freed");
     return CYTVDN_OK;
 }
 

@@ -422,7 +422,8 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
                                  ms if reference_data is not None else None, done, tm))
     if timing is not None:
         timing.update(setup_ms=tm[0], loop_ms=tm[1], finish_ms=tm[2], iters_fista=int(done[0]),
-                      iters_plain=int(done[1]), schedule={1: "two_pass", 2: "fused"}.get(int(done[2]), "none"))
+                      iters_plain=int(done[1]), schedule={1: "two_pass", 2: "fused"}.get(int(done[2]) & 0xff, "none"),
+                      pipeline_boxes=int(done[2]) >> 8)
     with np.errstate(all="ignore"):
         b_norm = np.array(bn[:n], dtype=np.float64).astype(dt)
         delta_recon = np.array(dl[:n], dtype=np.float64).astype(dt)

@@ -46,7 +46,7 @@ int main(void)
     double change = 0;
     for (size_t x = 0; x < n; ++x) change = fmax(change, fabs((double)recon[x] - data[x]));
     printf("%d FISTA iterations (schedule %d), loop %.3f ms, delta[0]=%.3e delta[last]=%.3e, max |recon-data| = %.2f\n",
-           done[0], done[2], ms[1], delta[0], delta[ITERS - 1], change);
+           done[0], done[2] & 0xff, ms[1], delta[0], delta[ITERS - 1], change);
     free(data); free(recon);
     return delta[ITERS - 1] < delta[0] ? 0 : 2;
 }

@@ -188,11 +188,22 @@ typedef struct cytvdn_denoise_params {
  * recon receives the result.  bnorm / delta: HOST arrays of iters_fista + iters_plain doubles
  * (entries of iterations that did not run stay 0, like the reference's trailing zeros);
  * mse: HOST array of that length + 1, or NULL when reference_data is NULL.
- * iters_done (3 ints): [0], [1] FISTA / unaccelerated iterations actually executed, [2] the schedule
- * that ran (1 two-pass, 2 fused).
+ * iters_done (3 ints): [0], [1] FISTA / unaccelerated iterations actually executed, [2] low byte: the
+ * schedule that ran (1 two-pass, 2 fused); bits 8..: number of boxes of the PCIe pipeline, 0 = not pipelined.
  * timing_ms (may be NULL): [0] allocation + host->device, [1] iteration loop (CUDA events),
- * [2] device->host + free.
+ * [2] device->host + free.  In a pipelined run the copies overlap the loop and are part of [1].
  * The call is synchronous.
+ *
+ * PCIe pipeline (host `data` and/or host `recon`, fused schedule, bc_mode 2, no stopping test, no
+ * reference_data, arrays >= 256 MB): the array is cut into 16 boxes of axis-0 planes; the first and last 16
+ * iterations run box by box in wavefront order, so a box starts iterating when it (and the next one) has
+ * arrived and is copied back when ITS last iteration is done.  The reconstruction is bit-identical to the
+ * unpipelined run for finite data; bnorm/delta are summed box by box in double (fixed order).  The wrap term of
+ * the last plane of axis 0 -- identically 0 under the Jia-Zhao boundary -- is taken as 0 instead of being
+ * recomputed from plane 0, so a NaN/Inf in plane 0 does not reach the last plane as it would in the reference.
+ * Environment CYTVDN_PIPELINE=0 disables it, =N (N >= 2) forces N boxes whatever the size.
+ *
+ * CYTVDN_TRACE=1 prints host-clock milestones of the call on stderr.
  */
 int cytvdn_denoise(const cytvdn_denoise_params *params, const void *data, void *recon,
                    const void *reference_data, double *bnorm, double *delta, double *mse,

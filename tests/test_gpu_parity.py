@@ -822,3 +822,62 @@ def test_peer_schedule_equals_single_gpu(tv, world, periodic, iters):
     assert np.array_equal(got.cpu().numpy(), ref[0])
     np.testing.assert_allclose(bn, ref[1].astype(np.float64), rtol=1e-5)
     np.testing.assert_allclose(dl, ref[2].astype(np.float64), rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape,dt,iters,fista", [
+    ((37, 5, 6, 16), "float32", 50, True),       # 16 boxes of 2-3 planes, wavefront at both ends + whole sweeps
+    ((37, 5, 6, 16), "float32", [9, 8], True),   # hybrid: the FISTA -> plain switch falls inside a wavefront
+    ((12, 7, 5, 13), "float32", 7, False),       # fewer iterations than boxes; rows padded (2-D box copies)
+    ((9, 6, 22), "float64", 40, True),           # 3-D, 4 boxes
+    ((64, 3, 4, 8), "float64", 3, True),
+])
+@pytest.mark.parametrize("boxes", [16, 3])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_pcie_pipeline_equals_unpipelined(tv, shape, dt, iters, fista, boxes, pinned, monkeypatch):
+    """Host arrays: upload / iterate / download overlapped box by box (wavefront order over (box, iteration)).
+    The reconstruction must be bit-identical to the unpipelined run, the per-iteration sums equal to 1e-12."""
+    rng = np.random.default_rng(sum(shape))
+    data = counts(rng, shape, dt)
+    if pinned:
+        h = tv.pinned_empty(shape, np.dtype(dt))
+        h[...] = data
+        data = h
+    mu = np.array([1, 1, .5, .5][:len(shape)] if len(shape) == 4 else [1, 1, .5], dtype=dt)
+    fn = tv.denoise4D if len(shape) == 4 else tv.denoise3D
+    monkeypatch.setenv("CYTVDN_PIPELINE", "0")
+    t0 = {}
+    ref = fn(data, mu, iters, FISTA=fista, quiet=True, schedule="fused", timing=t0)
+    monkeypatch.setenv("CYTVDN_PIPELINE", str(boxes))
+    t1 = {}
+    out = tv.pinned_empty(shape, np.dtype(dt)) if pinned else None
+    got = fn(data, mu, iters, FISTA=fista, quiet=True, schedule="fused", timing=t1, out=out)
+    assert t0["pipeline_boxes"] == 0 and t1["pipeline_boxes"] == min(boxes, shape[0] // 2)
+    assert np.array_equal(got[0], ref[0])
+    np.testing.assert_allclose(got[1].astype(np.float64), ref[1].astype(np.float64), rtol=1e-6)
+    np.testing.assert_allclose(got[2].astype(np.float64), ref[2].astype(np.float64), rtol=1e-6)
+    # cases the pipeline must decline: periodic boundary, stopping test, reference_data, device arrays
+    t2 = {}
+    fn(data, mu, 5, FISTA=fista, BC_mode=0, quiet=True, schedule="fused", timing=t2)
+    assert t2["pipeline_boxes"] == 0
+    fn(data, mu, 5, FISTA=fista, stopping_relative_change=1e-9, quiet=True, schedule="fused", timing=t2)
+    assert t2["pipeline_boxes"] == 0
+    fn(data, mu, 5, FISTA=fista, reference_data=np.asarray(data), quiet=True, schedule="fused", timing=t2)
+    assert t2["pipeline_boxes"] == 0
+
+
+def test_pcie_pipeline_default_threshold(tv):
+    """>= 256 MB host arrays are pipelined by default; the result equals the device-resident run bit for bit."""
+    import torch
+    from cytvdn_b200 import synth
+    x = synth.stem4d_device((128, 64, 128, 128), seed=5, counts=300.0)         # 512 MB
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    host = tv.pinned_empty(tuple(x.shape), np.float32)
+    torch.from_numpy(host).copy_(x)
+    out = tv.pinned_empty(tuple(x.shape), np.float32)
+    tm = {}
+    got = tv.denoise4D(host, mu, 40, True, quiet=True, out=out, timing=tm)
+    assert tm["pipeline_boxes"] == 16 and tm["schedule"] == "fused"
+    ref = tv.denoise4D(x, mu, 40, True, quiet=True, schedule="fused")
+    assert np.array_equal(got[0], ref[0].cpu().numpy())
+    np.testing.assert_allclose(got[1], ref[1], rtol=1e-6)
+    np.testing.assert_allclose(got[2], ref[2], rtol=1e-6)
