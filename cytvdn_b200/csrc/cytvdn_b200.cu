@@ -358,7 +358,8 @@ int check_common(int dtype, const void *a, const double *out_dev)
 // ---- half-step B -------------------------------------------------------------------------------
 template <typename T>
 int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const void *const *b,
-            const double *w, int zero_wrap, double *sums_dev, const cytvdn_step_opts *opts, cudaStream_t st)
+            const double *w, int zero_wrap, bool self_wrap, double *sums_dev, const cytvdn_step_opts *opts,
+            cudaStream_t st)
 {
     DcuParams<T> P;
     memset(&P, 0, sizeof P);
@@ -370,6 +371,7 @@ int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const 
         P.b[s] = (const T *)b[k];
         P.w[s] = (T)w[k];
         if ((zero_wrap >> k) & 1) P.zero_wrap |= 1 << s;
+        if (self_wrap) P.self_wrap |= 1 << s;
     }
     const int vw = pick_vw<T>(D.pitch, pb);
     if (int rc = make_sweep(D, vw, sizeof(T), opts, 2 + D.ndim, &P.S)) return rc;
@@ -548,7 +550,8 @@ int cytvdn_accumulator_update(int ndim, const int64_t *shape, int dtype, const v
     if (int rc = make_dims(ndim, shape, &c.D, opts)) return rc;
     if (int rc = check_common(dtype, a, norm_dev)) return rc;
     if (ax < 0 || ax >= ndim) return fail(CYTVDN_E_INVALID, "ax=%d out of range for ndim=%d", ax, ndim);
-    if (bc_mode < 0 || bc_mode > 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1 or 2");
+    if (bc_mode < 0 || bc_mode > 3) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1, 2 or 3");
+    if (bc_mode == 3) bc_mode = 1;                    // half-step A of the clamped mirror is the reference's mirror
     if (bc_mode == 1 && shape[ax] < 2) return fail(CYTVDN_E_INVALID, "mirror boundary needs extent >= 2 on axis %d", ax);
     if (!b) return fail(CYTVDN_E_INVALID, "b is NULL");
     const int s = c.D.axmap[ax];
@@ -587,7 +590,8 @@ int cytvdn_accumulator_update_all(int ndim, const int64_t *shape, int dtype, con
     if (int rc = make_dims(ndim, shape, &c.D, opts)) return rc;
     if (int rc = check_common(dtype, a, norm_dev)) return rc;
     if (!b || !clip) return fail(CYTVDN_E_INVALID, "b / clip is NULL");
-    if (bc_mode < 0 || bc_mode > 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1 or 2");
+    if (bc_mode < 0 || bc_mode > 3) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 1, 2 or 3");
+    if (bc_mode == 3) bc_mode = 1;
     if (ndim == 3 && (iso_R || iso_Q)) return fail(CYTVDN_E_INVALID, "half-isotropic update exists for 4-D only");
     for (int k = 0; k < ndim; ++k) {
         const int s = c.D.axmap[k];
@@ -615,12 +619,14 @@ int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void
     if (!recon_in || !recon_out || !b || !lambda_mu) return fail(CYTVDN_E_INVALID, "recon / b / lambda_mu is NULL");
     if (bc_mode == 1)
         return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=1 (mirror) is undefined behaviour in the reference's "
-                                          "datacube_update (utils.pyx:117-120) and is not implemented");
-    if (bc_mode != 0 && bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
+                                          "datacube_update (utils.pyx:117-120) and is not implemented; "
+                                          "BC_mode=3 is the well-defined (clamped-index) mirror");
+    if (bc_mode != 0 && bc_mode != 2 && bc_mode != 3) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 2 or 3");
     const int zw = opts ? opts->zero_wrap_mask : 0;
+    const bool sw = bc_mode == 3;
     return dtype == CYTVDN_F32
-               ? run_dcu<float>(D, orig, recon_in, recon_out, b, lambda_mu, zw, sums_dev, opts, (cudaStream_t)stream)
-               : run_dcu<double>(D, orig, recon_in, recon_out, b, lambda_mu, zw, sums_dev, opts, (cudaStream_t)stream);
+               ? run_dcu<float>(D, orig, recon_in, recon_out, b, lambda_mu, zw, sw, sums_dev, opts, (cudaStream_t)stream)
+               : run_dcu<double>(D, orig, recon_in, recon_out, b, lambda_mu, zw, sw, sums_dev, opts, (cudaStream_t)stream);
 }
 
 int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void *orig, const void *recon_in,
@@ -638,6 +644,8 @@ int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void
     if (bc_mode == 1)
         return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=1 (mirror) is undefined behaviour in the reference's "
                                           "datacube_update (utils.pyx:117-120) and is not implemented");
+    if (bc_mode == 3)
+        return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=3 (clamped mirror) runs on the two-pass schedule only");
     if (bc_mode != 0 && bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
     for (int k = 0; k < ndim; ++k) {
         const int s = c.D.axmap[k];
@@ -703,8 +711,16 @@ static int validate_params(const cytvdn_denoise_params *p, Dims *D)
     if (p->iters_fista < 0 || p->iters_plain < 0) return fail(CYTVDN_E_INVALID, "negative iteration count");
     if (p->bc_mode == 1)
         return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=1 (mirror) is undefined behaviour in the reference's "
-                                          "datacube_update (utils.pyx:117-120) and is not implemented");
-    if (p->bc_mode != 0 && p->bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
+                                          "datacube_update (utils.pyx:117-120) and is not implemented; "
+                                          "BC_mode=3 is the well-defined (clamped-index) mirror");
+    if (p->bc_mode != 0 && p->bc_mode != 2 && p->bc_mode != 3) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 2 or 3");
+    if (p->bc_mode == 3) {
+        if (p->isotropic_R || p->isotropic_Q)
+            return fail(CYTVDN_E_INVALID, "BC_mode=3 (mirror) exists for the anisotropic update only "
+                                          "(the half-isotropic kernels know the Jia-Zhao boundary only, halfisotropic.pyx:63-95)");
+        for (int k = 0; k < p->ndim; ++k)
+            if (p->shape[k] < 2) return fail(CYTVDN_E_INVALID, "mirror boundary needs extent >= 2 on axis %d", k);
+    }
     if (p->ndim == 3 && (p->isotropic_R || p->isotropic_Q))
         return fail(CYTVDN_E_INVALID, "half-isotropic update exists for 4-D only");
     return CYTVDN_OK;
@@ -836,7 +852,8 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     {
         const int want = requested_schedule(p);
         if (want == 2 && !fused_possible(p))
-            return fail(CYTVDN_E_INVALID, "the fused schedule does not cover half-isotropic updates; use schedule 0 or 1");
+            return fail(CYTVDN_E_INVALID, "the fused schedule covers neither half-isotropic updates nor the mirror "
+                                          "boundary (BC_mode 3); use schedule 0 or 1");
         if (want != 1 && fused_possible(p) && nIt > 0) {
             size_t free_b = 0, tot_b = 0;
             CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));

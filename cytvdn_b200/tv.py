@@ -353,7 +353,8 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
 
     if BC_mode == 1:
         raise NotImplementedError("BC_mode=1 (mirror) is undefined behaviour in the reference's datacube_update "
-                                  "(utils.pyx:117-120) and is not implemented")
+                                  "(utils.pyx:117-120) and is not implemented; BC_mode=3 is the well-defined "
+                                  "(clamped-index) mirror")
     _lib.require_gpu()
 
     P = DenoiseParams()
@@ -444,7 +445,9 @@ def denoise4D(datacube, mu, iterations=10, FISTA=True, stopping_relative_change=
     Drop-in for ``cyTVDN.denoise4D`` (`cyTVDN/cyTVDN.py:19-247`): same arguments in the same order,
     same assertions, returns ``(recon, b_norm, delta_recon[, MSE])`` with ``b_norm``/``delta_recon`` of
     length ``iterations`` (trailing zeros after an early stop).  ``iterations`` may be ``[n_FISTA,
-    n_unaccelerated]``.  ``BC_mode=1`` raises (undefined behaviour in the reference).
+    n_unaccelerated]``.  ``BC_mode=1`` raises (undefined behaviour in the reference); ``BC_mode=3`` (not in the
+    reference) is the well-defined mirror: half-step A as the reference's mirror (`anisotropic.pyx:69-70`), half-step
+    B with the forward index of `utils.pyx:117-120` clamped to ``min(i+1, N-1)``; anisotropic only.
 
     Extras (keyword only): ``out`` -- array/tensor that receives ``recon`` (e.g. ``pinned_empty``);
     ``timing`` -- dict filled with setup/loop/finish milliseconds measured with CUDA events;

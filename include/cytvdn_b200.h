@@ -17,9 +17,14 @@
  *    reductions are written as doubles to DEVICE memory (`*_dev`), never accumulated.
  *    Scalars that the reference casts to the array dtype at the call (clip, tk, lambda_mu)
  *    are passed as double and rounded to the array dtype inside, exactly like the reference.
- *  - bc_mode: 0 periodic, 1 mirror, 2 Jia-Zhao (anisotropic.pyx:20-24).  Mirror is only
- *    defined for the accumulator update; the reference's reconstruction update with
- *    bc_mode 1 reads out of bounds (utils.pyx:117-120) and is rejected here.
+ *  - bc_mode: 0 periodic, 1 mirror, 2 Jia-Zhao (anisotropic.pyx:20-24).  The reference's mirror is
+ *    only defined for the accumulator update (backward neighbour of index 0 is index 1,
+ *    anisotropic.pyx:69-70); its reconstruction update with bc_mode 1 reads out of bounds
+ *    (utils.pyx:117-120 take the forward index as max(i+1, N-1)) and is rejected here.
+ *    bc_mode 3 (CYTVDN_BC_MIRROR, NOT in the reference) is the well-defined reading of those lines:
+ *    accumulator update as bc_mode 1, reconstruction update with the forward index CLAMPED,
+ *    min(i+1, N-1), i.e. the term of an axis vanishes at its last index.  Anisotropic only,
+ *    two-pass schedule only, every extent >= 2.
  *  - Per-voxel arithmetic is bit-identical to the reference (separately rounded mul/add,
  *    IEEE division, comparison-based clip); only the reductions differ: they are
  *    accumulated in float64 (the reference's array-dtype sums are inaccurate).
@@ -37,6 +42,11 @@ extern "C" {
 
 #define CYTVDN_F32 0
 #define CYTVDN_F64 1
+
+#define CYTVDN_BC_PERIODIC 0
+#define CYTVDN_BC_MIRROR_A 1        /* the reference's mirror: accumulator update only */
+#define CYTVDN_BC_JIA_ZHAO 2
+#define CYTVDN_BC_MIRROR   3        /* clamped-index mirror, defined for both half-steps (extension) */
 
 #define CYTVDN_OK            0
 #define CYTVDN_E_INVALID     1      /* bad argument (message says which) */
@@ -130,7 +140,7 @@ int cytvdn_accumulator_update_all(int ndim, const int64_t *shape, int dtype, con
 
 /*
  * Half-step B.  Replaces datacube_update_4D utils.pyx:54-125 and datacube_update_3D
- * utils.pyx:131-199 (bc_mode 0 and 2 share one path there, :85/:163).
+ * utils.pyx:131-199 (bc_mode 0 and 2 share one path there, :85/:163; bc_mode 3: see the top of this file).
  * recon_out[x] = orig[x] - sum_k lambda_mu[k] * (b[k][x] - b[k][x + e_k mod N_k]),
  * summed left to right.  recon_in may equal recon_out (the reference updates in place).
  * sums_dev[0] = sum |recon_out - recon_in|, sums_dev[1] = sum |recon_in|; the reference
@@ -172,7 +182,7 @@ typedef struct cytvdn_denoise_params {
     int32_t iters_plain;        /* ... then unaccelerated ones (cyTVDN.py:98-108) */
     int32_t isotropic_R;        /* 4-D only */
     int32_t isotropic_Q;        /* 4-D only */
-    int32_t bc_mode;            /* 0 or 2 */
+    int32_t bc_mode;            /* 0, 2 or 3 (3: anisotropic, runs two-pass) */
     int32_t use_stopping;       /* stop a phase when delta < stopping_relative_change */
     double  stopping_relative_change;
     double  clip[4];            /* lambdaInv = 1/lam  (cyTVDN.py:77) */

@@ -162,12 +162,14 @@ DEF_ISO(tvo_iso_f64_D, double, double, fabs)
 /*   u[x] = f[x] - (((w0*(b0[x]-b0[x+e0 mod N0]) + w1*(...)) + w2*(...)) [+ w3*(...)])    */
 /*   delta += |u[x]-old| ; rnorm += |old| ;  returns the two sums (ratio taken by caller) */
 /* nterms = 3 for a 3-D array passed as (N0,N1,N2,1), 4 for 4-D.                          */
-/* BC_mode 1 is undefined behaviour in the reference (utils.pyx:117-120,192-197) and is   */
-/* not restated.                                                                          */
+/* BC_mode 1 is undefined behaviour in the reference (utils.pyx:117-120,192-197: the      */
+/* forward index is written max(i+1, N-1), which reads out of bounds) and is not restated.*/
+/* mirror != 0 is NOT reference behaviour: it is the evident intent of those lines, the   */
+/* forward index CLAMPED to min(i+1, N-1) -- the spec of this repo's BC_mode 3.           */
 /* ------------------------------------------------------------------------------------ */
 #define DEF_DCU(NAME, T, ACC, FABS)                                                         \
 void NAME(const T *f, T *u, const T *b0, const T *b1, const T *b2, const T *b3,             \
-          const T *w, const i64 *shape, int nterms, double *sums)                           \
+          const T *w, const i64 *shape, int nterms, int mirror, double *sums)               \
 {                                                                                           \
     const i64 n0 = shape[0], n1 = shape[1], n2 = shape[2], n3 = shape[3];                   \
     const i64 st[4] = { n1 * n2 * n3, n2 * n3, n3, 1 };                                     \
@@ -176,12 +178,12 @@ void NAME(const T *f, T *u, const T *b0, const T *b1, const T *b2, const T *b3, 
     _Pragma("omp parallel for reduction(+:delta,rnorm) schedule(static)")                   \
     for (i64 ij = 0; ij < rows; ++ij) {                                                     \
         const i64 i = ij / n1, j = ij % n1;                                                 \
-        const i64 f0 = (i + 1 == n0) ? -(n0 - 1) * st[0] : st[0];                           \
-        const i64 f1 = (j + 1 == n1) ? -(n1 - 1) * st[1] : st[1];                           \
+        const i64 f0 = (i + 1 == n0) ? (mirror ? 0 : -(n0 - 1) * st[0]) : st[0];            \
+        const i64 f1 = (j + 1 == n1) ? (mirror ? 0 : -(n1 - 1) * st[1]) : st[1];            \
         for (i64 k = 0; k < n2; ++k) {                                                      \
-            const i64 f2 = (k + 1 == n2) ? -(n2 - 1) * st[2] : st[2];                       \
+            const i64 f2 = (k + 1 == n2) ? (mirror ? 0 : -(n2 - 1) * st[2]) : st[2];        \
             for (i64 l = 0; l < n3; ++l) {                                                  \
-                const i64 f3 = (l + 1 == n3) ? -(n3 - 1) : 1;                               \
+                const i64 f3 = (l + 1 == n3) ? (mirror ? 0 : -(n3 - 1)) : 1;                \
                 const i64 x = ij * st[1] + k * n3 + l;                                      \
                 const T old = u[x];                                                         \
                 T s = (w[0] * (b0[x] - b0[x + f0])) + (w[1] * (b1[x] - b1[x + f1]));        \

@@ -65,7 +65,7 @@ def _load():
                 f.argtypes = [p, p, p, p, p, pi, C.c_int, C.c_int, t, t]
                 f = getattr(_lib, f"tvo_dcu_{sfx}_{acc}")
                 f.restype = None
-                f.argtypes = [p, p, p, p, p, p, p, pi, C.c_int, pd]
+                f.argtypes = [p, p, p, p, p, p, p, pi, C.c_int, C.c_int, pd]
                 f = getattr(_lib, f"tvo_sse_{sfx}_{acc}")
                 f.restype = C.c_double
                 f.argtypes = [p, p, C.c_int64]
@@ -115,6 +115,8 @@ class PortKernels:
 
     # anisotropic.pyx:17 / :89 / :169 / :243
     def accumulator_update(self, a, b, d, tk, ax, clip, BC_mode=2):
+        if BC_mode == 3:          # this repo's well-defined mirror: half-step A is the reference's BC_mode=1
+            BC_mode = 1
         if BC_mode == 1 and a.shape[ax] < 2:
             raise ValueError("mirror boundary needs extent >= 2")
         f = getattr(self.lib, f"tvo_acc_{_sfx(a)}_{self.acc}")
@@ -133,12 +135,13 @@ class PortKernels:
     def datacube_update_sums(self, orig, recon, bs, lambda_mu, BC_mode=2):
         if BC_mode == 1:
             raise ValueError("BC_mode=1 is undefined behaviour in the reference (utils.pyx:117-120)")
+        # BC_mode 3 (NOT in the reference): the forward index of utils.pyx:117-120 clamped, min(i+1, N-1)
         f = getattr(self.lib, f"tvo_dcu_{_sfx(orig)}_{self.acc}")
         w = np.ascontiguousarray(lambda_mu, dtype=orig.dtype)
         bs = list(bs) + [bs[0]] * (4 - len(bs))
         sums = (C.c_double * 2)()
         f(_ptr(orig), _ptr(recon), _ptr(bs[0]), _ptr(bs[1]), _ptr(bs[2]), _ptr(bs[3]), _ptr(w),
-          _shape4(orig), orig.ndim, sums)
+          _shape4(orig), orig.ndim, 1 if BC_mode == 3 else 0, sums)
         return float(sums[0]), float(sums[1])
 
     def datacube_update(self, orig, recon, bs, lambda_mu, BC_mode=2):
@@ -184,6 +187,8 @@ class ReferenceKernels:
 
     def accumulator_update(self, a, b, d, tk, ax, clip, BC_mode=2):
         t = a.dtype.type
+        if BC_mode == 3:          # this repo's mirror: half-step A is the reference's (well-defined) BC_mode=1
+            BC_mode = 1
         if a.ndim == 4:
             r = (self.an.accumulator_update_4D(a, b, ax, t(clip), BC_mode) if d is None else
                  self.an.accumulator_update_4D_FISTA(a, b, d, t(tk), ax, t(clip), BC_mode))
@@ -205,6 +210,8 @@ class ReferenceKernels:
         return float(np.abs((recon - old).astype(np.float64)).sum()), self._abs_sum(old)
 
     def _dcu(self, orig, recon, bs, lambda_mu, BC_mode):
+        if BC_mode not in (0, 2):     # 1: out-of-bounds reads in the reference; 3 does not exist there
+            raise ValueError(f"the reference's datacube_update is defined for BC_mode 0 and 2 only (got {BC_mode})")
         w = np.ascontiguousarray(lambda_mu, dtype=orig.dtype)
         if orig.ndim == 4:
             return self.ut.datacube_update_4D(orig, recon, bs[0], bs[1], bs[2], bs[3], w, BC_mode)

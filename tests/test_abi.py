@@ -129,7 +129,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.cytvdn_accumulator_update(4, sh4, 0, one, one, None, 0.0, 4, 1.0, 2, one, None, None) == 1
     assert "ax=4" in err()
     assert lib.cytvdn_accumulator_update(3, sh4, 0, one, one, None, 0.0, 3, 1.0, 2, one, None, None) == 1
-    assert lib.cytvdn_accumulator_update(4, sh4, 0, one, one, None, 0.0, 0, 1.0, 3, one, None, None) == 1
+    assert lib.cytvdn_accumulator_update(4, sh4, 0, one, one, None, 0.0, 0, 1.0, 4, one, None, None) == 1
     assert "BC_mode" in err()
     bad = (C.c_int64 * 4)(4, 0, 4, 4)
     assert lib.cytvdn_accumulator_update(4, bad, 0, one, one, None, 0.0, 0, 1.0, 2, one, None, None) == 1
@@ -160,6 +160,18 @@ def test_c_abi_argument_validation_without_gpu():
     two = C.c_void_p(32)
     P.bc_mode = 1
     assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 4
+    assert "BC_mode=3" in err()                        # the message points at the well-defined mirror
+    P.bc_mode, P.isotropic_Q = 3, 1
+    assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 1
+    assert "anisotropic update only" in err()
+    P.isotropic_Q, P.schedule = 0, 2
+    assert lib.cytvdn_fused_iteration(4, sh4, 0, one, one, one, bp, bp, None, None, 0.0, w, w, 3, one, None, None) == 4
+    assert "two-pass" in err()
+    P.schedule = 0
+    P.shape[2] = 1
+    assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 1
+    assert "extent >= 2 on axis 2" in err()
+    P.shape[2] = 4
     P.bc_mode, P.ndim, P.isotropic_R = 2, 3, 1
     assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 1
     assert "4-D only" in err()
