@@ -7,6 +7,8 @@
 #include "fused.cuh"
 #include "fused_tma.cuh"
 
+#include <sys/mman.h>
+
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -17,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -740,6 +743,7 @@ int requested_schedule(const cytvdn_denoise_params *p)
     if (env && *env) {
         if (!strcmp(env, "fused") || !strcmp(env, "2")) want = 2;
         else if (!strcmp(env, "two_pass") || !strcmp(env, "1")) want = 1;
+        else if (!strcmp(env, "streamed") || !strcmp(env, "3")) want = 3;
     }
     return want;
 }
@@ -802,6 +806,328 @@ struct Arena {
 };
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Out-of-core schedule: the arrays do not fit in HBM, host arrays in and out.
+//
+// Temporal blocking with overlapped tiles of axis-0 planes.  One PASS advances every voxel by K iterations: a tile
+// = `core` planes + K halo planes towards each neighbouring tile is copied in (state after m iterations), iterated K
+// times on a box that shrinks by one plane per iteration and side (a plane can be advanced only while both
+// neighbours hold the previous iterate), which leaves exactly the core at state m+K; the core is copied back.
+// Between passes the state (recon in the caller's `recon` array; b and d in pinned host arrays owned by the call)
+// lives on the host.  The first pass needs the input only (b = d = 0, recon = input), the last pass returns the
+// reconstruction only.  Two tile slots on the device: tile t+1 is copied in while tile t iterates; the copy back of
+// tile t waits for the copy in of tile t+1 because that one still reads t's core planes in their OLD state from
+// the same host arrays.  The schedule is PCIe bound by a wide margin (per pass and voxel the bus carries the whole
+// state in and out, the kernels need 1/7 of that time for K ~ 20 iterations), so what counts is K, i.e. planes per
+// slot: the tiles are iterated with the IN-PLACE two-pass kernels (10 arrays per slot for 4-D FISTA) rather than
+// the fused one (19) -- measured 1.9x faster end to end (tools/stream_bench.py).  Half-step A sweeps one plane more
+// than half-step B at the upper end (B reads the forward neighbour of b).  The kernels are the in-core ones (boxes,
+// owned-range sums, zero_wrap), so the reconstruction is bit-identical to the in-core run.
+// Jia-Zhao boundary, fixed iteration counts, no reference_data; anisotropic and half-isotropic.
+// ------------------------------------------------------------------------------------------------
+namespace {
+// Page-locked host memory.  cudaMallocHost pins 4 KB pages at ~2.4 GB/s (14 s for the 34 GB host state of a
+// config-3 sized out-of-core run).  Instead: an anonymous mapping advised to use transparent huge pages, faulted in
+// from all cores, then cudaHostRegister -- 1.9 s for the same 34 GB, same copy rates.  Falls back to cudaMallocHost
+// when the mapping or the registration fails; CYTVDN_HOST_ALLOC=cuda selects cudaMallocHost outright.
+std::mutex g_host_mu;
+std::map<void *, size_t> g_host_mapped;                  // allocations made by mmap + cudaHostRegister
+
+int pinned_alloc(void **out, size_t bytes)
+{
+    *out = nullptr;
+    const char *env = getenv("CYTVDN_HOST_ALLOC");
+    if (!(env && !strcmp(env, "cuda")) && bytes >= ((size_t)8 << 20)) {
+        const size_t len = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        void *q = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (q != MAP_FAILED) {
+            madvise(q, len, MADV_HUGEPAGE);
+            {   // fault the pages in (the kernel zeroes them) from all cores; registering then only pins
+                const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+                std::vector<std::thread> th;
+                const size_t chunk = ((len / hw) + 4095) & ~(size_t)4095;
+                for (unsigned i = 0; i < hw; ++i)
+                    th.emplace_back([=] {
+                        const size_t lo = (size_t)i * chunk, hi = std::min(len, lo + chunk);
+                        for (size_t x = lo; x < hi; x += 4096) ((volatile char *)q)[x] = 0;
+                    });
+                for (auto &t : th) t.join();
+            }
+            if (cudaHostRegister(q, len, cudaHostRegisterPortable) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_host_mu);
+                g_host_mapped[q] = len;
+                *out = q;
+                return CYTVDN_OK;
+            }
+            cudaGetLastError();
+            munmap(q, len);
+        }
+    }
+    cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(CYTVDN_E_NOMEM, "page-locked host allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return CYTVDN_OK;
+}
+
+int pinned_free(void *q)
+{
+    if (!q) return CYTVDN_OK;
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_host_mapped.find(q);
+        if (it != g_host_mapped.end()) { len = it->second; g_host_mapped.erase(it); }
+    }
+    if (len) {
+        cudaError_t e = cudaHostUnregister(q);
+        munmap(q, len);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(CYTVDN_E_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+        return CYTVDN_OK;
+    }
+    CUDA_TRY(cudaFreeHost(q));
+    return CYTVDN_OK;
+}
+
+struct HostPinned {
+    std::vector<void *> p;
+    ~HostPinned() { for (void *q : p) pinned_free(q); }
+    int alloc(void **out, size_t bytes)
+    {
+        if (int rc = pinned_alloc(out, bytes)) return rc;
+        p.push_back(*out);
+        return CYTVDN_OK;
+    }
+};
+
+int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *data, void *recon, double *bnorm,
+                     double *delta, int32_t *iters_done, double *timing_ms, size_t budget)
+{
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const int nd = p->ndim, nF = p->iters_fista, nU = p->iters_plain, M = nF + nU;
+    const size_t elem = p->dtype == CYTVDN_F32 ? 4 : 8;
+    const int64_t full_vw = 16 / (int64_t)elem;
+    const int64_t n0 = D.n[0], n3 = D.n[3], n3p = (n3 + full_vw - 1) / full_vw * full_vw;
+    const bool padded = n3p != n3;
+    const int64_t plane_rows = D.n[1] * D.n[2];
+    const size_t plane_b = (size_t)plane_rows * n3p * elem;           // one plane of an internal array
+    const bool fista = nF > 0;
+    const int arrays = 2 + nd * (fista ? 2 : 1);                      // f, recon, b (+ d)
+    if (M <= 0) return fail(CYTVDN_E_INVALID, "internal: streamed schedule without iterations");
+
+    // ---- tile geometry: P planes per slot, K iterations per pass, `core` = P - 2K planes advanced per tile ----
+    int64_t P = (int64_t)(budget / ((size_t)2 * arrays * plane_b));
+    if (P > n0) P = n0;
+    int64_t K, core;
+    if (P >= n0) { K = M; core = n0; }                                // one tile: nothing is recomputed
+    else {
+        if (P < 4)
+            return fail(CYTVDN_E_NOMEM, "out-of-core schedule: two tiles of 4 planes (%zu bytes) do not fit in the "
+                                        "device budget of %zu bytes", (size_t)2 * arrays * 4 * plane_b, budget);
+        K = std::max<int64_t>(1, P / 4);                              // minimises the traffic per iteration
+        if (K > M) K = M;
+        core = P - 2 * K;
+    }
+    const int nt = (int)((n0 + core - 1) / core);
+    const int npass = (int)((M + K - 1) / K);
+
+    Arena pool;
+    const size_t slot_b = (size_t)arrays * Arena::padded((size_t)P * plane_b);
+    const size_t nsums = (size_t)M * nt * 4;
+    if (int rc = pool.reserve(2 * slot_b + Arena::padded(nsums * sizeof(double)) + 4096)) return rc;
+    struct Slot { void *f, *r, *b[4], *d[4]; } slot[2];
+    memset(slot, 0, sizeof slot);
+    for (auto &sl : slot) {
+        if (int rc = pool.alloc(&sl.f, (size_t)P * plane_b)) return rc;
+        if (int rc = pool.alloc(&sl.r, (size_t)P * plane_b)) return rc;
+        for (int k = 0; k < nd; ++k) {
+            if (int rc = pool.alloc(&sl.b[k], (size_t)P * plane_b)) return rc;
+            if (fista) if (int rc = pool.alloc(&sl.d[k], (size_t)P * plane_b)) return rc;
+        }
+    }
+    double *sums_d = nullptr;
+    if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
+
+    // host state between passes (internal, padded layout); recon's host state is the caller's array
+    HostPinned hostmem;
+    void *hb[4] = {0, 0, 0, 0}, *hd[4] = {0, 0, 0, 0};
+    if (npass > 1)
+        for (int k = 0; k < nd; ++k) {
+            if (int rc = hostmem.alloc(&hb[k], (size_t)n0 * plane_b)) return rc;
+            if (fista && nF > K) if (int rc = hostmem.alloc(&hd[k], (size_t)n0 * plane_b)) return rc;
+        }
+
+    struct Streams {
+        cudaStream_t up = nullptr, comp = nullptr, down = nullptr;      // comp is the caller's stream (not owned)
+        cudaEvent_t up_done[2] = {0, 0}, comp_done[2] = {0, 0}, down_done[2] = {0, 0};
+        ~Streams()
+        {
+            for (int q = 0; q < 2; ++q) {
+                if (up_done[q]) cudaEventDestroy(up_done[q]);
+                if (comp_done[q]) cudaEventDestroy(comp_done[q]);
+                if (down_done[q]) cudaEventDestroy(down_done[q]);
+            }
+            if (up) cudaStreamDestroy(up);
+            if (down) cudaStreamDestroy(down);
+        }
+    } S;
+    CUDA_TRY(cudaStreamCreateWithFlags(&S.up, cudaStreamNonBlocking));
+    S.comp = (cudaStream_t)p->stream;                 // kernels run on the caller's stream (its reduction workspace is cached)
+    CUDA_TRY(cudaStreamCreateWithFlags(&S.down, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+        CUDA_TRY(cudaEventCreateWithFlags(&S.up_done[q], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&S.comp_done[q], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&S.down_done[q], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaMemsetAsync(sums_d, 0, nsums * sizeof(double), S.comp));
+    CUDA_TRY(cudaStreamSynchronize(S.comp));
+
+    // planes [g0, g0 + np) of a dense caller array <-> planes [l0, ...) of an internal (padded) tile array
+    auto dense_to_tile = [&](void *tile, int64_t l0, const void *host, int64_t g0, int64_t np, cudaStream_t st) -> int {
+        char *dp = (char *)tile + (size_t)l0 * plane_b;
+        const char *sp = (const char *)host + (size_t)g0 * plane_rows * n3 * elem;
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
+        CUDA_TRY(cudaMemsetAsync(dp, 0, (size_t)np * plane_b, st));
+        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3p * elem, sp, (size_t)n3 * elem, (size_t)n3 * elem,
+                                   (size_t)(np * plane_rows), cudaMemcpyDefault, st));
+        return CYTVDN_OK;
+    };
+    auto tile_to_dense = [&](void *host, int64_t g0, const void *tile, int64_t l0, int64_t np, cudaStream_t st) -> int {
+        char *dp = (char *)host + (size_t)g0 * plane_rows * n3 * elem;
+        const char *sp = (const char *)tile + (size_t)l0 * plane_b;
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
+        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3 * elem, sp, (size_t)n3p * elem, (size_t)n3 * elem,
+                                   (size_t)(np * plane_rows), cudaMemcpyDefault, st));
+        return CYTVDN_OK;
+    };
+
+    std::vector<double> tkr(M, 0.0);
+    {
+        double tk = 1.0;
+        for (int i = 0; i < nF; ++i) {                          // cyTVDN.py:154-156
+            const double tk_new = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
+            tkr[i] = (tk - 1.0) / tk_new;
+            tk = tk_new;
+        }
+    }
+    const double setup_ms = ms_since(t_start);
+    const auto t_loop = std::chrono::steady_clock::now();
+
+    for (int pass = 0, m0 = 0; m0 < M; ++pass, m0 += (int)K) {
+        const int Kp = (int)std::min<int64_t>(K, M - m0);
+        const bool first = m0 == 0, last = m0 + Kp == M;
+        const bool need_d_in = fista && m0 < nF;                // a FISTA iteration of this pass reads d ...
+        const bool need_d_out = fista && m0 + Kp < nF;          // ... and one of a later pass will
+        auto ext_lo = [&](int t) { return std::max<int64_t>(0, (int64_t)t * core - Kp); };
+        auto ext_hi = [&](int t) { return std::min<int64_t>(n0, std::min<int64_t>(n0, (int64_t)(t + 1) * core) + Kp); };
+
+        auto upload = [&](int t) -> int {
+            Slot &sl = slot[t & 1];
+            const int64_t e0 = ext_lo(t), np = ext_hi(t) - e0;
+            CUDA_TRY(cudaStreamWaitEvent(S.up, S.down_done[t & 1], 0));      // the slot's previous tile has left
+            if (int rc = dense_to_tile(sl.f, 0, data, e0, np, S.up)) return rc;
+            if (!first) if (int rc = dense_to_tile(sl.r, 0, recon, e0, np, S.up)) return rc;
+            for (int k = 0; k < nd; ++k) {
+                if (first) {
+                    CUDA_TRY(cudaMemsetAsync(sl.b[k], 0, (size_t)np * plane_b, S.up));
+                    if (fista) CUDA_TRY(cudaMemsetAsync(sl.d[k], 0, (size_t)np * plane_b, S.up));
+                } else {
+                    CUDA_TRY(cudaMemcpyAsync(sl.b[k], (char *)hb[k] + (size_t)e0 * plane_b, (size_t)np * plane_b,
+                                             cudaMemcpyHostToDevice, S.up));
+                    if (need_d_in)
+                        CUDA_TRY(cudaMemcpyAsync(sl.d[k], (char *)hd[k] + (size_t)e0 * plane_b, (size_t)np * plane_b,
+                                                 cudaMemcpyHostToDevice, S.up));
+                }
+            }
+            CUDA_TRY(cudaEventRecord(S.up_done[t & 1], S.up));
+            return CYTVDN_OK;
+        };
+        auto compute = [&](int t) -> int {
+            Slot &sl = slot[t & 1];
+            const int64_t e0 = ext_lo(t), e1 = ext_hi(t), np = e1 - e0;
+            const int64_t c0 = (int64_t)t * core, c1 = std::min<int64_t>(n0, c0 + core);
+            int64_t shape[4];
+            for (int k = 0; k < nd; ++k) shape[k] = p->shape[k];
+            shape[0] = np;
+            CUDA_TRY(cudaStreamWaitEvent(S.comp, S.up_done[t & 1], 0));
+            for (int k = 0; k < Kp; ++k) {
+                const int m = m0 + k;
+                cytvdn_step_opts o;
+                memset(&o, 0, sizeof o);
+                o.row_pitch = n3p;
+                o.box_lo[0] = e0 > 0 ? k + 1 : 0;
+                o.box_hi[0] = e1 < n0 ? np - (k + 1) : np;
+                o.own_lo[0] = c0 - e0;
+                o.own_hi[0] = c1 - e0;
+                if (e1 == n0 && e0 > 0) o.zero_wrap_mask = 1;   // plane 0 of b_0 is identically 0 under Jia-Zhao
+                const bool fi = m < nF;
+                const void *uin = (first && k == 0) ? sl.f : sl.r;      // recon = datacube.copy(), cyTVDN.py:145
+                double *sm = sums_d + ((size_t)m * nt + t) * 4;
+                cytvdn_step_opts oa = o;                                // A: one plane more at the upper end
+                if (e1 < n0) oa.box_hi[0] = o.box_hi[0] + 1;
+                oa.zero_wrap_mask = 0;
+                if (int rc = cytvdn_accumulator_update_all(nd, shape, p->dtype, uin, sl.b, fi ? sl.d : nullptr, tkr[m], p->clip,
+                                                           p->isotropic_R, p->isotropic_Q, p->bc_mode, sm, &oa, S.comp))
+                    return rc;
+                if (int rc = cytvdn_datacube_update(nd, shape, p->dtype, sl.f, uin, sl.r, sl.b, p->lambda_mu, p->bc_mode,
+                                                    sm + 1, &o, S.comp))
+                    return rc;
+            }
+            CUDA_TRY(cudaEventRecord(S.comp_done[t & 1], S.comp));
+            return CYTVDN_OK;
+        };
+        auto download = [&](int t) -> int {
+            Slot &sl = slot[t & 1];
+            const int64_t e0 = ext_lo(t);
+            const int64_t c0 = (int64_t)t * core, c1 = std::min<int64_t>(n0, c0 + core);
+            CUDA_TRY(cudaStreamWaitEvent(S.down, S.comp_done[t & 1], 0));
+            if (t + 1 < nt) CUDA_TRY(cudaStreamWaitEvent(S.down, S.up_done[(t + 1) & 1], 0));   // it read our old core
+            if (int rc = tile_to_dense(recon, c0, sl.r, c0 - e0, c1 - c0, S.down)) return rc;
+            if (!last)
+                for (int k = 0; k < nd; ++k) {
+                    CUDA_TRY(cudaMemcpyAsync((char *)hb[k] + (size_t)c0 * plane_b, (char *)sl.b[k] + (size_t)(c0 - e0) * plane_b,
+                                             (size_t)(c1 - c0) * plane_b, cudaMemcpyDeviceToHost, S.down));
+                    if (need_d_out)
+                        CUDA_TRY(cudaMemcpyAsync((char *)hd[k] + (size_t)c0 * plane_b, (char *)sl.d[k] + (size_t)(c0 - e0) * plane_b,
+                                                 (size_t)(c1 - c0) * plane_b, cudaMemcpyDeviceToHost, S.down));
+                }
+            CUDA_TRY(cudaEventRecord(S.down_done[t & 1], S.down));
+            return CYTVDN_OK;
+        };
+
+        if (int rc = upload(0)) return rc;
+        for (int t = 0; t < nt; ++t) {
+            if (t + 1 < nt) if (int rc = upload(t + 1)) return rc;
+            if (int rc = compute(t)) return rc;
+            if (int rc = download(t)) return rc;
+        }
+        // the next pass reads what this one wrote (tile 0 reaches into the cores of tiles 0 and 1)
+        CUDA_TRY(cudaStreamSynchronize(S.down));
+        CUDA_TRY(cudaStreamSynchronize(S.up));
+    }
+    const double loop_ms = ms_since(t_loop);
+    const auto t_fin = std::chrono::steady_clock::now();
+
+    std::vector<double> sums_h(nsums, 0.0);
+    CUDA_TRY(cudaMemcpy(sums_h.data(), sums_d, nsums * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < M; ++i) {
+        double s3[3] = {0.0, 0.0, 0.0};
+        for (int t = 0; t < nt; ++t)                            // fixed order: deterministic
+            for (int q = 0; q < 3; ++q) s3[q] += sums_h[((size_t)i * nt + t) * 4 + q];
+        bnorm[i] = s3[0];
+        delta[i] = s3[1] / s3[2];
+    }
+    if (iters_done) { iters_done[0] = nF; iters_done[1] = nU; iters_done[2] = 3 | (nt << 8); }
+    if (timing_ms) { timing_ms[0] = setup_ms; timing_ms[1] = loop_ms; timing_ms[2] = ms_since(t_fin); }
+    return CYTVDN_OK;
+}
+}  // namespace
+
 int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon, const void *reference_data,
                    double *bnorm, double *delta, double *mse, int32_t *iters_done, double *timing_ms)
 {
@@ -846,6 +1172,27 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         ~Restore() { now(); }
     } restore{prev_dev};
     cudaStream_t st = (cudaStream_t)p->stream;
+
+    // ---- out of core: host arrays whose state does not fit in HBM (or schedule 3 / CYTVDN_STREAM_BUDGET_MB) ----
+    {
+        bool want = requested_schedule(p) == 3;
+        size_t budget = 0;
+        { const char *env = getenv("CYTVDN_STREAM_BUDGET_MB"); if (env && atof(env) > 0) { budget = (size_t)(atof(env) * 1048576.0); want = true; } }
+        const bool can = !data_dev && !recon_dev && p->bc_mode == 2 && !p->use_stopping && !reference_data && nIt > 0;
+        size_t free_b = 0, tot_b = 0;
+        if (can || want) CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+        if (!want && can && requested_schedule(p) == 0) {
+            const int64_t in_core = arrays_needed(p, false, false, false, false) * (int64_t)nb;     // two-pass, in place
+            want = in_core + (int64_t)(512ll << 20) > (int64_t)free_b;
+        }
+        if (want) {
+            if (!can)
+                return fail(CYTVDN_E_UNSUPPORTED, "the out-of-core schedule needs host arrays in and out, BC_mode 2, at "
+                                                  "least one iteration, no stopping test and no reference_data");
+            if (!budget) budget = free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : free_b / 2;
+            return denoise_streamed(p, D, data, recon, bnorm, delta, iters_done, timing_ms, budget);
+        }
+    }
 
     // ---- schedule: fused single pass when it applies and the second state set fits ----------------
     bool fused = false;
@@ -1170,10 +1517,9 @@ int cytvdn_host_alloc(void **ptr, int64_t bytes)
     if (!ptr || bytes < 0) return fail(CYTVDN_E_INVALID, "bad argument");
     *ptr = nullptr;
     if (bytes == 0) return CYTVDN_OK;
-    CUDA_TRY(cudaMallocHost(ptr, (size_t)bytes));
-    return CYTVDN_OK;
+    return pinned_alloc(ptr, (size_t)bytes);
 }
-int cytvdn_host_free(void *ptr) { if (ptr) CUDA_TRY(cudaFreeHost(ptr)); return CYTVDN_OK; }
+int cytvdn_host_free(void *ptr) { return pinned_free(ptr); }
 int cytvdn_memcpy(void *dst, const void *src, int64_t bytes, void *stream)
 {
     if (bytes <= 0) return CYTVDN_OK;

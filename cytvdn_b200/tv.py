@@ -369,7 +369,7 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
     P.use_stopping = int(stopping_relative_change is not None)
     P.stopping_relative_change = float(stopping_relative_change) if stopping_relative_change is not None else 0.0
     P.device = -1
-    P.schedule = {None: 0, "auto": 0, "two_pass": 1, "fused": 2}[schedule]
+    P.schedule = {None: 0, "auto": 0, "two_pass": 1, "fused": 2, "streamed": 3}[schedule]
     P.stream = None
 
     device = None
@@ -423,8 +423,10 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
                                  ms if reference_data is not None else None, done, tm))
     if timing is not None:
         timing.update(setup_ms=tm[0], loop_ms=tm[1], finish_ms=tm[2], iters_fista=int(done[0]),
-                      iters_plain=int(done[1]), schedule={1: "two_pass", 2: "fused"}.get(int(done[2]) & 0xff, "none"),
-                      pipeline_boxes=int(done[2]) >> 8)
+                      iters_plain=int(done[1]),
+                      schedule={1: "two_pass", 2: "fused", 3: "streamed"}.get(int(done[2]) & 0xff, "none"),
+                      pipeline_boxes=(int(done[2]) >> 8) if (int(done[2]) & 0xff) != 3 else 0,
+                      stream_tiles=(int(done[2]) >> 8) if (int(done[2]) & 0xff) == 3 else 0)
     with np.errstate(all="ignore"):
         b_norm = np.array(bn[:n], dtype=np.float64).astype(dt)
         delta_recon = np.array(dl[:n], dtype=np.float64).astype(dt)
@@ -453,6 +455,8 @@ def denoise4D(datacube, mu, iterations=10, FISTA=True, stopping_relative_change=
     ``timing`` -- dict filled with setup/loop/finish milliseconds measured with CUDA events;
     ``schedule`` -- ``"fused"`` (one pass per iteration, 76 B/voxel, needs a second set of accumulator
     arrays), ``"two_pass"`` (96 B/voxel, in place) or ``None``: fused when it applies and fits in memory.
+    ``"streamed"``: out of core -- host arrays larger than the GPU's memory are iterated tile by tile (temporal
+    blocking over PCIe, `DESIGN.md` section 4); chosen automatically when nothing else fits.
     All schedules give bit-identical results.
     """
     return _denoise(4, datacube, mu, iterations, FISTA, stopping_relative_change, isotropic_R, isotropic_Q,

@@ -189,7 +189,8 @@ typedef struct cytvdn_denoise_params {
     double  lambda_mu[4];       /* lam/mu             (cyTVDN.py:78) */
     int32_t device;             /* device to run on when `data` is a host pointer; -1 = current */
     int32_t schedule;           /* 0 auto, 1 two passes per iteration (in place), 2 fused single pass
-                                   (out of place, second set of b/d arrays; anisotropic only) */
+                                   (out of place, second set of b/d arrays; anisotropic only), 3 out of core
+                                   (host arrays, tiles streamed over PCIe; see cytvdn_denoise) */
     void   *stream;             /* NULL = default stream */
 } cytvdn_denoise_params;
 
@@ -214,6 +215,17 @@ typedef struct cytvdn_denoise_params {
  * Environment CYTVDN_PIPELINE=0 disables it, =N (N >= 2) forces N boxes whatever the size.
  *
  * CYTVDN_TRACE=1 prints host-clock milestones of the call on stderr.
+ *
+ * Out of core (schedule 3; chosen by schedule 0 when `data` and `recon` are host arrays and not even the in-place
+ * schedule fits in the free device memory): temporal blocking with overlapped tiles of axis-0 planes.  A pass
+ * advances all voxels by K iterations: a tile (core + K halo planes per side) is copied in, iterated K times on a
+ * box shrinking by one plane per iteration and side, its core copied back; between passes recon lives in the
+ * caller's `recon`, b and d in pinned host arrays owned by the call (2 ndim arrays of the input's size with
+ * FISTA).  Two tile slots, copy-in of tile t+1 under the iterations of tile t; the tiles are iterated with the
+ * in-place two-pass kernels (fewest arrays per slot = most iterations per pass; the schedule is PCIe bound).
+ * Needs bc_mode 2, no stopping test, no reference_data (half-isotropic is fine); reconstruction bit-identical to
+ * the in-core schedules.  iters_done[2] = 3 | (tiles << 8); timing_ms from the host clock.  CYTVDN_STREAM_BUDGET_MB=N
+ * forces this schedule with N MB of device memory (testing / benchmarking).
  */
 int cytvdn_denoise(const cytvdn_denoise_params *params, const void *data, void *recon,
                    const void *reference_data, double *bnorm, double *delta, double *mse,
@@ -239,7 +251,9 @@ int cytvdn_synth_counts(const int64_t *gshape, int64_t offset0, int64_t lshape0,
 /* Small helpers so that a ctypes host needs no other CUDA binding. */
 int cytvdn_malloc(void **ptr, int64_t bytes);
 int cytvdn_free(void *ptr);
-int cytvdn_host_alloc(void **ptr, int64_t bytes);      /* pinned host memory */
+/* pinned host memory: huge-page mapping faulted in from all cores + cudaHostRegister (about 7x faster than
+   cudaMallocHost for multi-GB buffers), cudaMallocHost as fallback or with CYTVDN_HOST_ALLOC=cuda */
+int cytvdn_host_alloc(void **ptr, int64_t bytes);
 int cytvdn_host_free(void *ptr);
 int cytvdn_memcpy(void *dst, const void *src, int64_t bytes, void *stream);   /* any direction */
 int cytvdn_memset(void *dst, int value, int64_t bytes, void *stream);

@@ -881,3 +881,58 @@ def test_pcie_pipeline_default_threshold(tv):
     assert np.array_equal(got[0], ref[0].cpu().numpy())
     np.testing.assert_allclose(got[1], ref[1], rtol=1e-6)
     np.testing.assert_allclose(got[2], ref[2], rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape,dt,iters,fista,budget_planes,iso", [
+    ((41, 5, 6, 16), "float32", 23, True, 12, False),      # P=12: K=3, core 6 -> 7 tiles, 8 passes
+    ((41, 5, 6, 16), "float32", [7, 6], True, 16, False),  # FISTA -> plain switch inside a pass; d dropped afterwards
+    ((30, 4, 5, 13), "float32", 9, False, 8, False),       # rows padded, unaccelerated
+    ((26, 6, 22), "float64", 12, True, 9, False),          # 3-D
+    ((10, 3, 4, 8), "float64", 5, True, 100, False),       # budget larger than the array: one tile, one pass
+    ((64, 2, 3, 8), "float32", 4, True, 40, False),        # fewer iterations than K: single pass, several tiles
+    ((33, 6, 5, 12), "float32", 14, True, 12, True),       # half-isotropic (both pairs)
+])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_out_of_core_schedule_equals_in_core(tv, shape, dt, iters, fista, budget_planes, iso, pinned, monkeypatch):
+    """temporal blocking over PCIe with a forced tiny device budget; bit-identical recon."""
+    rng = np.random.default_rng(sum(shape) + budget_planes)
+    data = counts(rng, shape, dt)
+    if pinned:
+        h = tv.pinned_empty(shape, np.dtype(dt))
+        h[...] = data
+        data = h
+    nd = len(shape)
+    mu = np.array([1, 1, .5, .5] if nd == 4 else [1, 1, .5], dtype=dt)
+    fn = tv.denoise4D if nd == 4 else tv.denoise3D
+    monkeypatch.setenv("CYTVDN_PIPELINE", "0")
+    kw = dict(isotropic_R=True, isotropic_Q=True) if iso else {}
+    ref = fn(data, mu, iters, FISTA=fista, quiet=True, schedule="two_pass" if iso else "fused", **kw)
+    # device budget = budget_planes planes per slot: 2 slots x (2 + nd * (2 if FISTA else 1)) arrays
+    elem = np.dtype(dt).itemsize
+    vwf = 16 // elem
+    n3p = (shape[-1] + vwf - 1) // vwf * vwf
+    plane_b = int(np.prod(shape[1:-1])) * n3p * elem
+    any_fista = fista or isinstance(iters, list)
+    arrays = 2 + nd * (2 if any_fista else 1)
+    monkeypatch.setenv("CYTVDN_STREAM_BUDGET_MB", repr((2 * arrays * plane_b * budget_planes + 4096) / 1048576.0))
+    tm = {}
+    out = tv.pinned_empty(shape, np.dtype(dt)) if pinned else None
+    got = fn(data, mu, iters, FISTA=fista, quiet=True, timing=tm, out=out, **kw)
+    assert tm["schedule"] == "streamed"
+    P = min(budget_planes, shape[0])
+    if P >= shape[0]:
+        assert tm["stream_tiles"] == 1
+    else:
+        core = P - 2 * max(1, min(P // 4, sum(iters) if isinstance(iters, list) else iters))
+        assert tm["stream_tiles"] == -(-shape[0] // core)
+    assert np.array_equal(got[0], ref[0]), float(np.abs(got[0] - ref[0]).max())
+    np.testing.assert_allclose(got[1].astype(np.float64), ref[1].astype(np.float64), rtol=1e-6)
+    np.testing.assert_allclose(got[2].astype(np.float64), ref[2].astype(np.float64), rtol=1e-6)
+    # the schedule declines what it cannot do
+    with pytest.raises(Exception, match="out-of-core schedule needs"):
+        fn(data, mu, 3, FISTA=fista, BC_mode=0, quiet=True)
+    with pytest.raises(Exception, match="out-of-core schedule needs"):
+        fn(data, mu, 3, FISTA=fista, stopping_relative_change=1e-3, quiet=True)
+    monkeypatch.setenv("CYTVDN_STREAM_BUDGET_MB", repr(2 * arrays * plane_b * 3 / 1048576.0))
+    with pytest.raises(Exception, match="do not fit"):
+        fn(data, mu, 3, FISTA=fista, quiet=True)
