@@ -58,7 +58,14 @@ template <typename T, int VW, bool FISTA, bool AX2, bool PEER>
 #define FUSED_MINB_PLAIN 3      // 3-D unaccelerated variant: few arrays, 3 CTAs per SM fit without spills (measured
                                 // +17..60 %); the 4-D unaccelerated variant would spill and was measured slower
 #endif
+#ifdef FUSED_MAXNREG           // experiment knob: cap the registers directly instead of through CTAs per SM.
+                               // Measured (config 3, 13.4 ms base): 192 threads x 3 CTAs at 112 regs 14.9 ms,
+                               // at 104 regs 18.4 ms, 128 threads x 5 CTAs at 96 regs 18.3 ms -- more resident
+                               // threads do not help, spills hurt.
+__global__ void __maxnreg__(FUSED_MAXNREG)
+#else
 __global__ void __launch_bounds__(kBlock, ((!FISTA && !AX2) ? FUSED_MINB_PLAIN : FUSED_MINB))
+#endif
 tv_fused_kernel(const FusedParams<T> P)
 {
     const Sweep &S = P.S;
