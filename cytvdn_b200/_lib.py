@@ -81,6 +81,8 @@ PROTOTYPES = {
     "cytvdn_denoise": (C.c_int, [C.POINTER(DenoiseParams), _vp, _vp, _vp, _dp, _dp, _dp,
                                  C.POINTER(C.c_int32), _dp]),
     "cytvdn_denoise_workspace_bytes": (C.c_int, [C.POINTER(DenoiseParams), C.c_int, C.c_int, _i64p]),
+    "cytvdn_pipeline_schedule": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64, _i64p]),
+    "cytvdn_stream_plan": (C.c_int, [C.POINTER(DenoiseParams), C.c_int64, _i64p]),
     "cytvdn_synth_counts": (C.c_int, [_i64p, C.c_int64, C.c_int64, C.c_int, _vp, _vp, C.c_double, C.c_uint64,
                                       _vp, _vp]),
     "cytvdn_malloc": (C.c_int, [_vpp, C.c_int64]),

@@ -807,6 +807,69 @@ struct Arena {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+// Host-side plans of the two PCIe schedules.  Pure functions (no CUDA): cytvdn_denoise runs exactly what they
+// return, and the CPU tests check their invariants through cytvdn_pipeline_schedule / cytvdn_stream_plan.
+// ------------------------------------------------------------------------------------------------
+namespace {
+// PCIe pipeline: the order of (box, iteration) launches for `n_iter` iterations over `nbox` boxes of axis-0 planes;
+// box -1 = a sweep of the whole array.  The first and the last `nbox` iterations run as wavefronts: step t runs
+// iteration m0 + (t - c) of box c, higher boxes first, so that box c+1 has finished iteration m-1 before box c
+// starts iteration m (and box c-1, one iteration ahead, has not yet overwritten what box c still reads).
+void pipeline_schedule(int nbox, int n_iter, std::vector<std::pair<int, int>> &out)
+{
+    out.clear();
+    auto wave = [&](int m0, int m1) {
+        const int depth = m1 - m0;
+        for (int t = 0; t < nbox + depth - 1; ++t)
+            for (int c = std::min(t, nbox - 1); c >= 0 && t - c < depth; --c) out.push_back({c, m0 + (t - c)});
+    };
+    const int depth = nbox;
+    if (n_iter <= 2 * depth + 2) wave(0, n_iter);
+    else {
+        wave(0, depth);
+        for (int m = depth; m < n_iter - depth; ++m) out.push_back({-1, m});
+        wave(n_iter - depth, n_iter);
+    }
+}
+
+// Out-of-core schedule: tile geometry for a device budget.
+struct StreamPlan {
+    int64_t planes_per_slot;   // P: axis-0 planes one tile slot holds
+    int64_t iters_per_pass;    // K
+    int64_t core_planes;       // planes a tile advances by K iterations (= P - 2K, or the whole axis)
+    int64_t tiles, passes;
+    int64_t arrays_per_slot;   // f, recon, b (+ d)
+    int64_t plane_bytes;       // one axis-0 plane of an internal (row-padded) array
+    int64_t host_state_bytes;  // page-locked host arrays the call allocates (b, d between passes)
+};
+int make_stream_plan(const cytvdn_denoise_params *p, const Dims &D, size_t budget, StreamPlan *sp)
+{
+    const int nd = p->ndim, nF = p->iters_fista, M = p->iters_fista + p->iters_plain;
+    const int64_t elem = p->dtype == CYTVDN_F32 ? 4 : 8, full_vw = 16 / elem;
+    const int64_t n0 = D.n[0], n3p = (D.n[3] + full_vw - 1) / full_vw * full_vw;
+    sp->plane_bytes = D.n[1] * D.n[2] * n3p * elem;
+    sp->arrays_per_slot = 2 + nd * (nF > 0 ? 2 : 1);
+    if (M <= 0) return fail(CYTVDN_E_INVALID, "the out-of-core schedule needs at least one iteration");
+    int64_t P = (int64_t)(budget / ((size_t)2 * sp->arrays_per_slot * sp->plane_bytes));
+    if (P >= n0) { P = n0; sp->iters_per_pass = M; sp->core_planes = n0; }      // one tile: nothing is recomputed
+    else {
+        if (P < 4)
+            return fail(CYTVDN_E_NOMEM, "out-of-core schedule: two tiles of 4 planes (%lld bytes) do not fit in the "
+                                        "device budget of %zu bytes", (long long)(2 * sp->arrays_per_slot * 4 * sp->plane_bytes), budget);
+        sp->iters_per_pass = std::min<int64_t>(M, std::max<int64_t>(1, P / 4));     // P/4 minimises the traffic per iteration
+        sp->core_planes = P - 2 * sp->iters_per_pass;
+    }
+    sp->planes_per_slot = P;
+    sp->tiles = (n0 + sp->core_planes - 1) / sp->core_planes;
+    sp->passes = (M + sp->iters_per_pass - 1) / sp->iters_per_pass;
+    sp->host_state_bytes = 0;
+    if (sp->passes > 1)
+        sp->host_state_bytes = (int64_t)nd * (1 + ((nF > 0 && nF > sp->iters_per_pass) ? 1 : 0)) * n0 * sp->plane_bytes;
+    return CYTVDN_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
 // Out-of-core schedule: the arrays do not fit in HBM, host arrays in and out.
 //
 // Temporal blocking with overlapped tiles of axis-0 planes.  One PASS advances every voxel by K iterations: a tile
@@ -917,27 +980,16 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
     const int64_t plane_rows = D.n[1] * D.n[2];
     const size_t plane_b = (size_t)plane_rows * n3p * elem;           // one plane of an internal array
     const bool fista = nF > 0;
-    const int arrays = 2 + nd * (fista ? 2 : 1);                      // f, recon, b (+ d)
-    if (M <= 0) return fail(CYTVDN_E_INVALID, "internal: streamed schedule without iterations");
 
     // ---- tile geometry: P planes per slot, K iterations per pass, `core` = P - 2K planes advanced per tile ----
-    int64_t P = (int64_t)(budget / ((size_t)2 * arrays * plane_b));
-    if (P > n0) P = n0;
-    int64_t K, core;
-    if (P >= n0) { K = M; core = n0; }                                // one tile: nothing is recomputed
-    else {
-        if (P < 4)
-            return fail(CYTVDN_E_NOMEM, "out-of-core schedule: two tiles of 4 planes (%zu bytes) do not fit in the "
-                                        "device budget of %zu bytes", (size_t)2 * arrays * 4 * plane_b, budget);
-        K = std::max<int64_t>(1, P / 4);                              // minimises the traffic per iteration
-        if (K > M) K = M;
-        core = P - 2 * K;
-    }
-    const int nt = (int)((n0 + core - 1) / core);
-    const int npass = (int)((M + K - 1) / K);
+    StreamPlan sp;
+    if (int rc = make_stream_plan(p, D, budget, &sp)) return rc;
+    const int64_t P = sp.planes_per_slot, K = sp.iters_per_pass, core = sp.core_planes;
+    const int nt = (int)sp.tiles;
+    const int npass = (int)sp.passes;
 
     Arena pool;
-    const size_t slot_b = (size_t)arrays * Arena::padded((size_t)P * plane_b);
+    const size_t slot_b = (size_t)sp.arrays_per_slot * Arena::padded((size_t)P * plane_b);
     const size_t nsums = (size_t)M * nt * 4;
     if (int rc = pool.reserve(2 * slot_b + Arena::padded(nsums * sizeof(double)) + 4096)) return rc;
     struct Slot { void *f, *r, *b[4], *d[4]; } slot[2];
@@ -1423,31 +1475,18 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
                                           b[in], b[out], fi ? d[in] : nullptr, fi ? d[out] : nullptr, tkr[m], p->clip,
                                           p->lambda_mu, p->bc_mode, sums_d + ((size_t)m * nbox + (c < 0 ? 0 : c)) * 4, &o, st);
         };
-        // iterations [m0, m1) of every box; within a step t = box + (iteration - m0) the higher boxes go first,
-        // so that box c+1 has finished iteration m-1 before box c starts iteration m
-        auto wave = [&](int m0, int m1, bool first, bool last) -> int {
-            const int depth = m1 - m0;
-            for (int t = 0; t < nbox + depth - 1; ++t) {
-                for (int c = std::min(t, nbox - 1); c >= 0 && t - c < depth; --c) {
-                    const int m = m0 + (t - c);
-                    if (first && m == 0 && !data_dev) {         // needs the planes of boxes c and c+1
-                        const int need = std::min(c + 1, nbox - 1);
-                        for (; uploaded <= need; ++uploaded) if (int rc = upload_box(uploaded)) return rc;
-                        CUDA_TRY(cudaStreamWaitEvent(st, side.up[need], 0));
-                    }
-                    if (int rc = iterate(m, c)) return rc;
-                    if (last && m == nIt - 1 && !recon_dev) CUDA_TRY(cudaEventRecord(side.down[c], st));
-                }
+        // first and last `nbox` iterations box by box in wavefront order, whole-array sweeps in between
+        std::vector<std::pair<int, int>> order;
+        pipeline_schedule(nbox, nIt, order);
+        for (const auto &cm : order) {
+            const int c = cm.first, m = cm.second;
+            if (c >= 0 && m == 0 && !data_dev) {                // needs the planes of boxes c and c+1
+                const int need = std::min(c + 1, nbox - 1);
+                for (; uploaded <= need; ++uploaded) if (int rc = upload_box(uploaded)) return rc;
+                CUDA_TRY(cudaStreamWaitEvent(st, side.up[need], 0));
             }
-            return CYTVDN_OK;
-        };
-        const int depth = nbox;
-        if (nIt <= 2 * depth + 2) {
-            if (int rc = wave(0, nIt, true, true)) return rc;
-        } else {
-            if (int rc = wave(0, depth, true, false)) return rc;
-            for (int m = depth; m < nIt - depth; ++m) if (int rc = iterate(m, -1)) return rc;
-            if (int rc = wave(nIt - depth, nIt, false, true)) return rc;
+            if (int rc = iterate(m, c)) return rc;
+            if (c >= 0 && m == nIt - 1 && !recon_dev) CUDA_TRY(cudaEventRecord(side.down[c], st));
         }
         for (int i = 0; i < nIt; ++i) ran[i] = 1;
         done[0] = nF; done[1] = nU;
@@ -1499,6 +1538,32 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     pool.release();
     pool0.release();
     mark("arenas freed");
+    return CYTVDN_OK;
+}
+
+// ---- host-side plans (no GPU needed) ------------------------------------------------------------
+int cytvdn_pipeline_schedule(int nbox, int n_iter, int32_t *box, int32_t *iter, int64_t capacity, int64_t *count)
+{
+    if (nbox < 1 || n_iter < 0 || !count) return fail(CYTVDN_E_INVALID, "bad argument");
+    std::vector<std::pair<int, int>> order;
+    pipeline_schedule(nbox, n_iter, order);
+    *count = (int64_t)order.size();
+    if (box && iter) {
+        if (capacity < *count) return fail(CYTVDN_E_INVALID, "capacity %lld < %lld launches", (long long)capacity, (long long)*count);
+        for (size_t i = 0; i < order.size(); ++i) { box[i] = order[i].first; iter[i] = order[i].second; }
+    }
+    return CYTVDN_OK;
+}
+
+int cytvdn_stream_plan(const cytvdn_denoise_params *p, int64_t budget_bytes, int64_t *out8)
+{
+    Dims D;
+    if (int rc = validate_params(p, &D)) return rc;
+    if (!out8 || budget_bytes <= 0) return fail(CYTVDN_E_INVALID, "bad argument");
+    StreamPlan sp;
+    if (int rc = make_stream_plan(p, D, (size_t)budget_bytes, &sp)) return rc;
+    out8[0] = sp.planes_per_slot; out8[1] = sp.iters_per_pass; out8[2] = sp.core_planes; out8[3] = sp.tiles;
+    out8[4] = sp.passes; out8[5] = sp.arrays_per_slot; out8[6] = sp.plane_bytes; out8[7] = sp.host_state_bytes;
     return CYTVDN_OK;
 }
 

@@ -236,6 +236,26 @@ int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *params, int data
                                    int recon_on_device, int64_t *bytes);
 
 /*
+ * Host-side plans of the two PCIe schedules of cytvdn_denoise (pure functions, no GPU needed; the call runs exactly
+ * what they return -- exported so that the schedules can be checked without a device).
+ *
+ * cytvdn_pipeline_schedule: launch order of the PCIe pipeline for `n_iter` iterations over `nbox` boxes of axis-0
+ * planes: pairs (box, iteration), box -1 = one sweep of the whole array.  *count receives the number of launches;
+ * box / iter (capacity entries each) may be NULL to query the count.  Invariant: when (c, m) runs, (c-1, m-1),
+ * (c, m-1) and (c+1, m-1) have run, and (c-1, m+1), (c, m+1), (c+1, m+1) have not (iteration m reads state set
+ * m%2 of the three boxes and writes set (m+1)%2 of box c).
+ *
+ * cytvdn_stream_plan: tile geometry of the out-of-core schedule for a device budget: out8 = { planes per tile
+ * slot P, iterations per pass K, core planes per tile (P - 2K, or the whole axis when it fits), tiles, passes,
+ * arrays per slot, bytes of one axis-0 plane of an internal array, bytes of page-locked host state the call
+ * allocates }.  Tile t of a pass of Kp iterations holds planes [max(0, t*core - Kp), min(N0, (t+1)*core + Kp));
+ * iteration k of the pass sweeps that range shrunk by k+1 planes on every side that is not an end of the array.
+ */
+int cytvdn_pipeline_schedule(int nbox, int n_iter, int32_t *box, int32_t *iter, int64_t capacity,
+                             int64_t *count);
+int cytvdn_stream_plan(const cytvdn_denoise_params *params, int64_t budget_bytes, int64_t *out8);
+
+/*
  * Deterministic synthetic 4D-STEM-like counts for benchmarks and sharded parity runs
  * (SURVEY.md section 8d): out[x] = max(0, rint(c + sqrt(c) * z(x))) with
  * c = counts * scan_mod[i,j] * templ[k,l] + 0.02 * counts and z an approximately normal
