@@ -853,9 +853,12 @@ int make_stream_plan(const cytvdn_denoise_params *p, const Dims &D, size_t budge
     int64_t P = (int64_t)(budget / ((size_t)2 * sp->arrays_per_slot * sp->plane_bytes));
     if (P >= n0) { P = n0; sp->iters_per_pass = M; sp->core_planes = n0; }      // one tile: nothing is recomputed
     else {
+        // two slots of P planes + the carry buffer (2K = P/2 planes): 2.5 P planes of every array
+        P = (int64_t)(budget / ((size_t)5 * sp->arrays_per_slot * sp->plane_bytes / 2));
         if (P < 4)
-            return fail(CYTVDN_E_NOMEM, "out-of-core schedule: two tiles of 4 planes (%lld bytes) do not fit in the "
-                                        "device budget of %zu bytes", (long long)(2 * sp->arrays_per_slot * 4 * sp->plane_bytes), budget);
+            return fail(CYTVDN_E_NOMEM, "out-of-core schedule: two tiles of 4 planes and their carry buffer (%lld bytes) do "
+                                        "not fit in the device budget of %zu bytes",
+                        (long long)(10 * sp->arrays_per_slot * sp->plane_bytes), budget);
         sp->iters_per_pass = std::min<int64_t>(M, std::max<int64_t>(1, P / 4));     // P/4 minimises the traffic per iteration
         sp->core_planes = P - 2 * sp->iters_per_pass;
     }
@@ -878,9 +881,10 @@ int make_stream_plan(const cytvdn_denoise_params *p, const Dims &D, size_t budge
 // neighbours hold the previous iterate), which leaves exactly the core at state m+K; the core is copied back.
 // Between passes the state (recon in the caller's `recon` array; b and d in pinned host arrays owned by the call)
 // lives on the host.  The first pass needs the input only (b = d = 0, recon = input), the last pass returns the
-// reconstruction only.  Two tile slots on the device: tile t+1 is copied in while tile t iterates; the copy back of
-// tile t waits for the copy in of tile t+1 because that one still reads t's core planes in their OLD state from
-// the same host arrays.  The schedule is PCIe bound by a wide margin (per pass and voxel the bus carries the whole
+// reconstruction only.  Two tile slots on the device: tile t+1 is copied in while tile t iterates.  The 2K planes
+// two neighbouring tiles share are not copied in twice: they are saved (device to device) into a carry buffer
+// before tile t starts to iterate and handed to tile t+1, so every plane crosses the bus once per pass and the copy
+// in of tile t+1 never reads host planes that the copy back of tile t overwrites.  The schedule is PCIe bound by a wide margin (per pass and voxel the bus carries the whole
 // state in and out, the kernels need 1/7 of that time for K ~ 20 iterations), so what counts is K, i.e. planes per
 // slot: the tiles are iterated with the IN-PLACE two-pass kernels (10 arrays per slot for 4-D FISTA) rather than
 // the fused one (19) -- measured 1.9x faster end to end (tools/stream_bench.py).  Half-step A sweeps one plane more
@@ -991,17 +995,25 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
     Arena pool;
     const size_t slot_b = (size_t)sp.arrays_per_slot * Arena::padded((size_t)P * plane_b);
     const size_t nsums = (size_t)M * nt * 4;
-    if (int rc = pool.reserve(2 * slot_b + Arena::padded(nsums * sizeof(double)) + 4096)) return rc;
-    struct Slot { void *f, *r, *b[4], *d[4]; } slot[2];
+    // slot[2] is the CARRY buffer: the 2K planes two neighbouring tiles share are saved from tile t's slot before it
+    // starts iterating and handed to tile t+1, so that every plane crosses the bus once per pass
+    const int64_t carry_planes = nt > 1 ? 2 * K : 0;
+    const size_t carry_b = (size_t)sp.arrays_per_slot * Arena::padded((size_t)carry_planes * plane_b);
+    if (int rc = pool.reserve(2 * slot_b + carry_b + Arena::padded(nsums * sizeof(double)) + 4096)) return rc;
+    struct Slot { void *f, *r, *b[4], *d[4]; } slot[3];
     memset(slot, 0, sizeof slot);
-    for (auto &sl : slot) {
-        if (int rc = pool.alloc(&sl.f, (size_t)P * plane_b)) return rc;
-        if (int rc = pool.alloc(&sl.r, (size_t)P * plane_b)) return rc;
+    for (int q = 0; q < 3; ++q) {
+        Slot &sl = slot[q];
+        const size_t planes = q < 2 ? (size_t)P : (size_t)carry_planes;
+        if (planes == 0) continue;
+        if (int rc = pool.alloc(&sl.f, planes * plane_b)) return rc;
+        if (int rc = pool.alloc(&sl.r, planes * plane_b)) return rc;
         for (int k = 0; k < nd; ++k) {
-            if (int rc = pool.alloc(&sl.b[k], (size_t)P * plane_b)) return rc;
-            if (fista) if (int rc = pool.alloc(&sl.d[k], (size_t)P * plane_b)) return rc;
+            if (int rc = pool.alloc(&sl.b[k], planes * plane_b)) return rc;
+            if (fista) if (int rc = pool.alloc(&sl.d[k], planes * plane_b)) return rc;
         }
     }
+    Slot &carry = slot[2];
     double *sums_d = nullptr;
     if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
 
@@ -1041,6 +1053,7 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
 
     // planes [g0, g0 + np) of a dense caller array <-> planes [l0, ...) of an internal (padded) tile array
     auto dense_to_tile = [&](void *tile, int64_t l0, const void *host, int64_t g0, int64_t np, cudaStream_t st) -> int {
+        if (np <= 0) return CYTVDN_OK;
         char *dp = (char *)tile + (size_t)l0 * plane_b;
         const char *sp = (const char *)host + (size_t)g0 * plane_rows * n3 * elem;
         if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
@@ -1050,6 +1063,7 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
         return CYTVDN_OK;
     };
     auto tile_to_dense = [&](void *host, int64_t g0, const void *tile, int64_t l0, int64_t np, cudaStream_t st) -> int {
+        if (np <= 0) return CYTVDN_OK;
         char *dp = (char *)host + (size_t)g0 * plane_rows * n3 * elem;
         const char *sp = (const char *)tile + (size_t)l0 * plane_b;
         if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
@@ -1080,20 +1094,48 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
 
         auto upload = [&](int t) -> int {
             Slot &sl = slot[t & 1];
-            const int64_t e0 = ext_lo(t), np = ext_hi(t) - e0;
+            const int64_t e0 = ext_lo(t), e1 = ext_hi(t), np = e1 - e0;
+            // leading planes that tile t-1 also held: they wait in the carry buffer (saved below, same stream)
+            const int64_t have = t > 0 ? std::min(ext_hi(t - 1), e1) - e0 : 0;
+            const size_t hb_ = (size_t)have * plane_b, rest_b = (size_t)(np - have) * plane_b;
             CUDA_TRY(cudaStreamWaitEvent(S.up, S.down_done[t & 1], 0));      // the slot's previous tile has left
-            if (int rc = dense_to_tile(sl.f, 0, data, e0, np, S.up)) return rc;
-            if (!first) if (int rc = dense_to_tile(sl.r, 0, recon, e0, np, S.up)) return rc;
+            auto d2d = [&](void *dst, const void *src, size_t bytes) -> int {
+                if (bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, S.up));
+                return CYTVDN_OK;
+            };
+            if (int rc = d2d(sl.f, carry.f, hb_)) return rc;
+            if (int rc = dense_to_tile(sl.f, have, data, e0 + have, np - have, S.up)) return rc;
+            if (!first) {
+                if (int rc = d2d(sl.r, carry.r, hb_)) return rc;
+                if (int rc = dense_to_tile(sl.r, have, recon, e0 + have, np - have, S.up)) return rc;
+            }
             for (int k = 0; k < nd; ++k) {
                 if (first) {
                     CUDA_TRY(cudaMemsetAsync(sl.b[k], 0, (size_t)np * plane_b, S.up));
                     if (fista) CUDA_TRY(cudaMemsetAsync(sl.d[k], 0, (size_t)np * plane_b, S.up));
                 } else {
-                    CUDA_TRY(cudaMemcpyAsync(sl.b[k], (char *)hb[k] + (size_t)e0 * plane_b, (size_t)np * plane_b,
-                                             cudaMemcpyHostToDevice, S.up));
-                    if (need_d_in)
-                        CUDA_TRY(cudaMemcpyAsync(sl.d[k], (char *)hd[k] + (size_t)e0 * plane_b, (size_t)np * plane_b,
+                    if (int rc = d2d(sl.b[k], carry.b[k], hb_)) return rc;
+                    if (rest_b)
+                        CUDA_TRY(cudaMemcpyAsync((char *)sl.b[k] + hb_, (char *)hb[k] + (size_t)(e0 + have) * plane_b, rest_b,
                                                  cudaMemcpyHostToDevice, S.up));
+                    if (need_d_in) {
+                        if (int rc = d2d(sl.d[k], carry.d[k], hb_)) return rc;
+                        if (rest_b)
+                            CUDA_TRY(cudaMemcpyAsync((char *)sl.d[k] + hb_, (char *)hd[k] + (size_t)(e0 + have) * plane_b, rest_b,
+                                                     cudaMemcpyHostToDevice, S.up));
+                    }
+                }
+            }
+            if (t + 1 < nt) {       // save what tile t+1 shares with this one before the iterations change it
+                const int64_t s0 = ext_lo(t + 1) - e0, cnt = std::min(e1, ext_hi(t + 1)) - ext_lo(t + 1);
+                const size_t off = (size_t)s0 * plane_b, cb = (size_t)cnt * plane_b;
+                if (int rc = d2d(carry.f, (char *)sl.f + off, cb)) return rc;
+                if (!first) {
+                    if (int rc = d2d(carry.r, (char *)sl.r + off, cb)) return rc;
+                    for (int k = 0; k < nd; ++k) {
+                        if (int rc = d2d(carry.b[k], (char *)sl.b[k] + off, cb)) return rc;
+                        if (need_d_in) if (int rc = d2d(carry.d[k], (char *)sl.d[k] + off, cb)) return rc;
+                    }
                 }
             }
             CUDA_TRY(cudaEventRecord(S.up_done[t & 1], S.up));
@@ -1138,7 +1180,6 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
             const int64_t e0 = ext_lo(t);
             const int64_t c0 = (int64_t)t * core, c1 = std::min<int64_t>(n0, c0 + core);
             CUDA_TRY(cudaStreamWaitEvent(S.down, S.comp_done[t & 1], 0));
-            if (t + 1 < nt) CUDA_TRY(cudaStreamWaitEvent(S.down, S.up_done[(t + 1) & 1], 0));   // it read our old core
             if (int rc = tile_to_dense(recon, c0, sl.r, c0 - e0, c1 - c0, S.down)) return rc;
             if (!last)
                 for (int k = 0; k < nd; ++k) {
@@ -1158,7 +1199,8 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
             if (int rc = compute(t)) return rc;
             if (int rc = download(t)) return rc;
         }
-        // the next pass reads what this one wrote (tile 0 reaches into the cores of tiles 0 and 1)
+        // the next pass reads what this one wrote.  (Letting the passes run into each other -- per-tile events instead
+        // of this barrier -- was measured: no gain, the bus is busy either way.)
         CUDA_TRY(cudaStreamSynchronize(S.down));
         CUDA_TRY(cudaStreamSynchronize(S.up));
     }

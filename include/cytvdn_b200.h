@@ -221,7 +221,8 @@ typedef struct cytvdn_denoise_params {
  * advances all voxels by K iterations: a tile (core + K halo planes per side) is copied in, iterated K times on a
  * box shrinking by one plane per iteration and side, its core copied back; between passes recon lives in the
  * caller's `recon`, b and d in pinned host arrays owned by the call (2 ndim arrays of the input's size with
- * FISTA).  Two tile slots, copy-in of tile t+1 under the iterations of tile t; the tiles are iterated with the
+ * FISTA).  Two tile slots, copy-in of tile t+1 under the iterations of tile t, the planes two tiles share handed
+ * over on the device (carry buffer) so that every plane crosses the bus once per pass; the tiles are iterated with the
  * in-place two-pass kernels (fewest arrays per slot = most iterations per pass; the schedule is PCIe bound).
  * Needs bc_mode 2, no stopping test, no reference_data (half-isotropic is fine); reconstruction bit-identical to
  * the in-core schedules.  iters_done[2] = 3 | (tiles << 8); timing_ms from the host clock.  CYTVDN_STREAM_BUDGET_MB=N
@@ -245,8 +246,8 @@ int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *params, int data
  * (c, m-1) and (c+1, m-1) have run, and (c-1, m+1), (c, m+1), (c+1, m+1) have not (iteration m reads state set
  * m%2 of the three boxes and writes set (m+1)%2 of box c).
  *
- * cytvdn_stream_plan: tile geometry of the out-of-core schedule for a device budget: out8 = { planes per tile
- * slot P, iterations per pass K, core planes per tile (P - 2K, or the whole axis when it fits), tiles, passes,
+ * cytvdn_stream_plan: tile geometry of the out-of-core schedule for a device budget (two slots of P planes + a
+ * carry buffer of 2K planes of every array): out8 = { planes per tile slot P, iterations per pass K, core planes per tile (P - 2K, or the whole axis when it fits), tiles, passes,
  * arrays per slot, bytes of one axis-0 plane of an internal array, bytes of page-locked host state the call
  * allocates }.  Tile t of a pass of Kp iterations holds planes [max(0, t*core - Kp), min(N0, (t+1)*core + Kp));
  * iteration k of the pass sweeps that range shrunk by k+1 planes on every side that is not an end of the array.

@@ -919,12 +919,16 @@ def test_out_of_core_schedule_equals_in_core(tv, shape, dt, iters, fista, budget
     out = tv.pinned_empty(shape, np.dtype(dt)) if pinned else None
     got = fn(data, mu, iters, FISTA=fista, quiet=True, timing=tm, out=out, **kw)
     assert tm["schedule"] == "streamed"
-    P = min(budget_planes, shape[0])
-    if P >= shape[0]:
-        assert tm["stream_tiles"] == 1
-    else:
-        core = P - 2 * max(1, min(P // 4, sum(iters) if isinstance(iters, list) else iters))
-        assert tm["stream_tiles"] == -(-shape[0] // core)
+    import ctypes as C
+    from cytvdn_b200 import _lib
+    prm = _lib.DenoiseParams()
+    prm.ndim, prm.dtype, prm.bc_mode = nd, 0 if dt == "float32" else 1, 2
+    for k in range(nd):
+        prm.shape[k] = shape[k]
+    prm.iters_fista, prm.iters_plain = (iters if isinstance(iters, list) else ([iters, 0] if fista else [0, iters]))
+    plan = (C.c_int64 * 8)()
+    assert _lib.load().cytvdn_stream_plan(C.byref(prm), 2 * arrays * plane_b * budget_planes + 4096, plan) == 0
+    assert tm["stream_tiles"] == plan[3] and (plan[3] > 1 or budget_planes >= shape[0])
     assert np.array_equal(got[0], ref[0]), float(np.abs(got[0] - ref[0]).max())
     np.testing.assert_allclose(got[1].astype(np.float64), ref[1].astype(np.float64), rtol=1e-6)
     np.testing.assert_allclose(got[2].astype(np.float64), ref[2].astype(np.float64), rtol=1e-6)
@@ -933,6 +937,6 @@ def test_out_of_core_schedule_equals_in_core(tv, shape, dt, iters, fista, budget
         fn(data, mu, 3, FISTA=fista, BC_mode=0, quiet=True)
     with pytest.raises(Exception, match="out-of-core schedule needs"):
         fn(data, mu, 3, FISTA=fista, stopping_relative_change=1e-3, quiet=True)
-    monkeypatch.setenv("CYTVDN_STREAM_BUDGET_MB", repr(2 * arrays * plane_b * 3 / 1048576.0))
+    monkeypatch.setenv("CYTVDN_STREAM_BUDGET_MB", repr(2 * arrays * plane_b * 4 / 1048576.0))
     with pytest.raises(Exception, match="do not fit"):
         fn(data, mu, 3, FISTA=fista, quiet=True)

@@ -85,22 +85,24 @@ def stream_plan(shape, dtype, n_fista, n_plain, budget):
 @pytest.mark.parametrize("shape,dtype,nF,nU,planes", [
     ((41, 5, 6, 16), "float32", 23, 0, 12), ((41, 5, 6, 16), "float32", 7, 6, 16), ((30, 4, 5, 13), "float32", 0, 9, 8),
     ((26, 6, 22), "float64", 12, 0, 9), ((10, 3, 4, 8), "float64", 5, 0, 100), ((64, 2, 3, 8), "float32", 4, 0, 40),
-    ((1024, 1024, 128, 128), "float32", 100, 0, 70), ((256, 256, 128, 128), "float32", 100, 0, 4),
+    ((1024, 1024, 128, 128), "float32", 100, 0, 70), ((256, 256, 128, 128), "float32", 100, 0, 5),
 ])
 def test_stream_plan_geometry_and_replay(shape, dtype, nF, nU, planes):
-    """Replay the out-of-core schedule on version numbers per axis-0 plane: the host state is updated in place,
-    tile t+1 is copied in BEFORE tile t is copied back, a plane can be advanced only when both neighbours hold the
-    previous iterate."""
+    """Replay the out-of-core schedule on version numbers per axis-0 plane: the host state is updated in place, the
+    planes two tiles share travel through the carry buffer, a plane can be advanced only when both neighbours hold
+    the previous iterate."""
     nd, n0, M = len(shape), shape[0], nF + nU
     elem = 4 if dtype == "float32" else 8
     n3p = -(-shape[-1] // (16 // elem)) * (16 // elem)
     plane_b = int(np.prod(shape[1:-1])) * n3p * elem
     arrays = 2 + nd * (2 if nF else 1)
-    rc, g = stream_plan(shape, dtype, nF, nU, 2 * arrays * plane_b * planes + 1000)
+    budget = 2 * arrays * plane_b * planes + 1000
+    rc, g = stream_plan(shape, dtype, nF, nU, budget)
     assert rc == 0
     assert g["arrays"] == arrays and g["plane_bytes"] == plane_b
     P, K, core = g["P"], g["K"], g["core"]
-    assert P == min(planes, n0)
+    # the whole axis when two slots hold it, else two slots + the carry buffer (2K <= P/2 planes) within the budget
+    assert P == (n0 if planes >= n0 else budget // (5 * arrays * plane_b // 2))
     if P >= n0:
         assert (K, core, g["tiles"], g["passes"], g["host_bytes"]) == (M, n0, 1, 1, 0)
     else:
@@ -119,17 +121,29 @@ def test_stream_plan_geometry_and_replay(shape, dtype, nF, nU, planes):
             c0, c1 = t * core, min(n0, (t + 1) * core)
             tiles.append((max(0, c0 - Kp), min(n0, c1 + Kp), c0, c1))
         assert all(e1 - e0 <= P for e0, e1, _, _ in tiles)             # a tile fits its slot
-        loaded = {}
+        loaded, carry = {}, {}
 
         def upload(t):
+            """Planes shared with tile t-1 come from the carry buffer, the rest from the host state."""
             e0, e1, _, _ = tiles[t]
-            assert all(host[g_] == m0 for g_ in range(e0, e1)), f"tile {t} reads planes already advanced"
-            loaded[t] = {g_: m0 for g_ in range(e0, e1)}
+            have = min(tiles[t - 1][1], e1) - e0 if t > 0 else 0
+            assert 0 <= have <= 2 * K
+            st = {g_: carry[g_] for g_ in range(e0, e0 + have)}
+            for g_ in range(e0 + have, e1):
+                assert host[g_] == m0, f"tile {t} reads plane {g_} already advanced on the host"
+                st[g_] = host[g_]
+            assert all(v == m0 for v in st.values())
+            loaded[t] = st
+            carry.clear()
+            if t + 1 < len(tiles):                         # saved before tile t iterates
+                for g_ in range(tiles[t + 1][0], min(e1, tiles[t + 1][1])):
+                    carry[g_] = st[g_]
+                assert len(carry) <= 2 * K
 
         upload(0)
         for t, (e0, e1, c0, c1) in enumerate(tiles):
             if t + 1 < len(tiles):
-                upload(t + 1)                              # ... before tile t overwrites its core on the host
+                upload(t + 1)                              # runs ahead of the iterations of tile t
             st = loaded.pop(t)
             for k in range(Kp):
                 lo = e0 + (k + 1 if e0 > 0 else 0)
@@ -149,7 +163,7 @@ def test_stream_plan_geometry_and_replay(shape, dtype, nF, nU, planes):
 
 
 def test_stream_plan_errors():
-    rc, _ = stream_plan((41, 5, 6, 16), "float32", 10, 0, 100)          # not even two tiles of 4 planes
+    rc, _ = stream_plan((41, 5, 6, 16), "float32", 10, 0, 100)          # not even two tiles of 4 planes + carry
     assert rc == 3 and b"do not fit" in _lib.load().cytvdn_last_error()
     rc, _ = stream_plan((41, 5, 6, 16), "float32", 0, 0, 1 << 30)
     assert rc == 1
