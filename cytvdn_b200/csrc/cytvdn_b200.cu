@@ -1031,6 +1031,9 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
         cudaEvent_t up_done[2] = {0, 0}, comp_done[2] = {0, 0}, down_done[2] = {0, 0};
         ~Streams()
         {
+            // error paths leave copies in flight that reference the host state freed right after this object
+            if (up) cudaStreamSynchronize(up);
+            if (down) cudaStreamSynchronize(down);
             for (int q = 0; q < 2; ++q) {
                 if (up_done[q]) cudaEventDestroy(up_done[q]);
                 if (comp_done[q]) cudaEventDestroy(comp_done[q]);
