@@ -10,7 +10,9 @@ lambda itself (no ``mu/32`` default, `mpi.py:249-250`), the data are processed a
 ``BC_mode`` is 2 (`mpi.py:84`), every rank reads only its own block (owned planes + one overlap plane per
 neighbour, `mpi.py:165-180`) and writes only its owned block (`mpi.py:470-498`).
 
-File formats: ``.npy`` (memory-mapped, any size) in and out.  ``.h5`` / ``.emd`` input is read through h5py when
+File formats: ``.npy`` (memory-mapped, any size) in and out.  On one GPU the arrays stay on the host: the library
+overlaps the PCIe copies with the iterations and switches to its out-of-core schedule (``--schedule streamed`` forces
+it) when the state does not fit in the GPU's memory.  ``.h5`` / ``.emd`` input is read through h5py when
 that package is importable (dataset path ``-p``); the reference's ``.dm3/.dm4`` readers (py4DSTEM / ncempy) and
 its EMD v0.7 writer are out of scope.  Unlike the reference, FISTA (`mpi.py:310-311` "haven't done FISTA yet"),
 hybrid iteration counts and 3-D input (single GPU only) work, and ``--stop`` enables the relative-change stopping
@@ -51,7 +53,8 @@ def build_parser():
     p.add_argument("-p", "--dataset", default=None, help="HDF5 dataset path (h5/emd input)")
     p.add_argument("--stop", type=float, default=None, help="stopping_relative_change")
     p.add_argument("--grid", default="1d", choices=["1d", "mpi"], help="tile layout: axis-0 split or mpi.py's (wx, wy)")
-    p.add_argument("--schedule", default="auto", choices=["auto", "fused", "two_pass"])
+    p.add_argument("--schedule", default="auto", choices=["auto", "fused", "two_pass", "streamed"],
+                   help="streamed: out of core, one GPU only")
     return p
 
 
@@ -124,14 +127,18 @@ def main(argv=None):
     t0 = time.time()
 
     if world == 1:
-        block = torch.from_numpy(read_block(data, tuple(slice(None) for _ in range(ndim)))).to(dev)
+        # host arrays in and out: the library overlaps the PCIe copies with the iterations and, when the arrays do
+        # not fit in the GPU's memory, iterates them tile by tile (out-of-core schedule); the result is written
+        # straight into the memory-mapped output file
+        block = read_block(data, tuple(slice(None) for _ in range(ndim)))
         fn = tv.denoise4D if ndim == 4 else tv.denoise3D
-        kw = dict(iterations=iterations, FISTA=fista, stopping_relative_change=args.stop, lam=lam, quiet=True,
-                  schedule=None if args.schedule == "auto" else args.schedule)
-        recon, bn, dl = fn(block, mu, **kw)
         out = create_output(args.output[0], data.shape)
-        out[...] = recon.cpu().numpy()
+        tm = {}
+        kw = dict(iterations=iterations, FISTA=fista, stopping_relative_change=args.stop, lam=lam, quiet=True,
+                  schedule=None if args.schedule == "auto" else args.schedule, out=out, timing=tm)
+        recon, bn, dl = fn(block, mu, **kw)
         out.flush()
+        say(f"schedule: {tm.get('schedule')}" + (f", {tm['stream_tiles']} tiles" if tm.get("stream_tiles") else ""))
     else:
         if ndim != 4:
             raise SystemExit("sharded runs exist for 4-D data only (as in the reference, mpi.py:252-255); "
@@ -143,6 +150,8 @@ def main(argv=None):
             plan = sharded.ShardPlan(data.shape, world, rank, None if args.grid == "1d" else "mpi")
             say(f"Dividing work over a {plan.grid[0]} by {plan.grid[1]} grid...")
             block = torch.from_numpy(read_block(data, plan.read_global)).to(dev)
+            if args.schedule == "streamed":
+                raise SystemExit("--schedule streamed runs on one GPU only")
             recon, bn, dl = sharded.denoise4D_sharded(block, mu, iterations, fista, args.stop, plan=plan, lam=lam,
                                                       schedule=args.schedule)
             if head:

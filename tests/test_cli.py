@@ -60,3 +60,15 @@ def test_cli_single_gpu_matches_api(tmp_path):
     assert cli.main(argv) == 0
     ref = tv.denoise3D(c, mu3, [4, 3], lam=mu3 / 16, quiet=True)[0]
     assert np.array_equal(np.load(dst), ref)
+    # out-of-core from the command line: forced with a tiny device budget, same result
+    big = rng.poisson(rng.uniform(20, 400, (40, 5, 6, 16))).astype(np.float32)
+    np.save(src, big)
+    argv = ["-i", src, "-o", dst, "-d", "4", "-f", "1", "-n", "11", "-v", "0", "--schedule", "streamed", "-L"] + \
+           [str(float(v)) for v in lam] + ["-m"] + [str(float(v)) for v in mu]
+    os.environ["CYTVDN_STREAM_BUDGET_MB"] = repr(2.5 * 10 * 5 * 6 * 16 * 4 * 12 / 1048576.0 + 0.01)    # 12 planes per slot
+    try:
+        assert cli.main(argv) == 0
+    finally:
+        del os.environ["CYTVDN_STREAM_BUDGET_MB"]
+    ref = tv.denoise4D(big, mu, 11, True, lam=lam, quiet=True)[0]
+    assert np.array_equal(np.load(dst), ref)
