@@ -101,7 +101,7 @@ def run_in_process(gdata, mu, world, grid, n_fista, n_plain, K, periodic=False):
     return out, np.array(bn), np.array(dl)
 
 
-def run_distributed_rank(rank, world, port, grid, gshape, seed, n_fista, n_plain, outdir):
+def run_distributed_rank(rank, world, port, grid, gshape, seed, n_fista, n_plain, outdir, periodic=False):
     """One gloo rank (spawned by the test): product ``halo_exchange`` + oracle kernels."""
     import os
     import torch
@@ -116,8 +116,8 @@ def run_distributed_rank(rank, world, port, grid, gshape, seed, n_fista, n_plain
         rng = np.random.default_rng(seed)
         gdata = rng.poisson(rng.uniform(20, 400, gshape)).astype(np.float32)   # every rank builds the same array
         mu = np.array([1, 1, .5, .5], dtype=np.float32)
-        plan = ShardPlan(gshape, world, rank, grid)
-        sh = CpuShard(plan, np.ascontiguousarray(gdata[plan.read_global]), mu, O.PortKernels("D"), fista=n_fista > 0)
+        plan = ShardPlan(gshape, world, rank, grid, periodic)
+        sh = CpuShard(plan, np.ascontiguousarray(plan.extract(gdata)), mu, O.PortKernels("D"), fista=n_fista > 0)
         tensors = {k: torch.from_numpy(v) for k, v in sh.arrays.items()}      # share memory with the numpy state
         sums = []
         tk = 1.0

@@ -129,20 +129,22 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("grid", [None, (1, 2)])
-def test_gloo_world2_halo_exchange(grid):
+@pytest.mark.parametrize("grid,periodic", [(None, False), ((1, 2), False), (None, True), ((1, 2), True)])
+def test_gloo_world2_halo_exchange(grid, periodic):
     """Two real ranks over gloo: the product halo_exchange (axis-0 planes contiguous, axis-1 planes
-    staged) and the all-reduced owned sums."""
+    staged) and the all-reduced owned sums.  Periodic with two tiles: both neighbours of a rank are the SAME peer,
+    i.e. two messages per direction between one pair in one batch -- they must not be swapped."""
     import torch.multiprocessing as mp
     gshape, seed, nF, nU = (10, 9, 5, 4), 99, 6, 3
     with tempfile.TemporaryDirectory() as tmp:
         port = _free_port()
-        mp.spawn(drv.run_distributed_rank, args=(2, port, grid, gshape, seed, nF, nU, tmp), nprocs=2, join=True)
+        mp.spawn(drv.run_distributed_rank, args=(2, port, grid, gshape, seed, nF, nU, tmp, periodic), nprocs=2, join=True)
         rng = np.random.default_rng(seed)
         data = rng.poisson(rng.uniform(20, 400, gshape)).astype(np.float32)
         mu = np.array([1, 1, .5, .5], dtype=np.float32)
         O.set_threads(O.max_threads())
-        ref = O.denoise4D(data, mu, [nF, nU], quiet=True, kernels=O.PortKernels("D"), scalars="D")
+        ref = O.denoise4D(data, mu, [nF, nU], BC_mode=0 if periodic else 2, quiet=True, kernels=O.PortKernels("D"),
+                          scalars="D")
         got = np.empty_like(data)
         for r in range(2):
             z = np.load(os.path.join(tmp, f"rank{r}.npz"))
@@ -184,3 +186,55 @@ def test_periodic_plan_wraps():
     assert np.array_equal(p0.extract(g), g[[11, 0, 1, 2, 3, 4]])
     one = ShardPlan((12, 10, 3, 4), 1, 0, None, periodic=True)
     assert not one.has_lo[0] and one.jz_flags == 0 and one.local_shape == (12, 10, 3, 4)
+
+
+def _check_plan_family(gshape, world, grid, periodic):
+    """Invariants of all ranks' plans together: the owned blocks tile the array, every send has exactly one
+    matching receive on the peer and both name the same global plane, only owned planes are sent."""
+    plans = []
+    for r in range(world):
+        try:
+            plans.append(ShardPlan(gshape, world, r, grid, periodic))
+        except ValueError as e:                     # a split that leaves a tile empty is refused for every rank alike
+            assert "empty" in str(e) or "grid" in str(e) or "planes" in str(e), e
+            return False
+    cover = np.zeros(gshape[:2], dtype=int)
+    for p in plans:
+        cover[p.owned_global] += 1
+        assert tuple(p.extract(np.zeros(gshape, np.float32)).shape) == tuple(p.local_shape)
+    assert np.all(cover == 1)
+    for phase in ("after_a", "after_b", "after_fused"):
+        sends, recvs = {}, {}
+        for p in plans:
+            for op in getattr(p, phase)():
+                gidx = p.read_indices(op.axis)[op.index]          # global index of the plane
+                key = (min(p.rank, op.peer), max(p.rank, op.peer), op.array, op.axis, gidx,
+                       p.rank if op.kind == "send" else op.peer)
+                (sends if op.kind == "send" else recvs).setdefault(key, 0)
+                (sends if op.kind == "send" else recvs)[key] += 1
+                if op.kind == "send":
+                    lo, hi = p.valid[op.axis]
+                    assert lo <= gidx < hi, "only owned planes are sent"
+        assert sends == recvs, f"{phase}: unmatched {set(sends) ^ set(recvs)}"
+    return True
+
+
+def test_plan_invariants_random():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(2, 40), st.integers(2, 40), st.integers(1, 8), st.booleans(), st.sampled_from(["1d", "mpi", "2d"]),
+           st.integers(1, 4))
+    def run(n0, n1, world, periodic, kind, wx):
+        gshape = (n0, n1, 2, 3)
+        if kind == "1d":
+            grid = None
+        elif kind == "mpi":
+            grid = "mpi"
+        else:
+            if world % wx:
+                return
+            grid = (wx, world // wx)
+        _check_plan_family(gshape, world, grid, periodic)
+
+    run()
