@@ -39,7 +39,7 @@ if ROOT not in sys.path:
 
 import numpy as np
 
-METRIC = "tv4d_fista_gvoxel_iter_per_s"
+METRIC = "4D TV-FISTA Gvoxel-iter/s"        # BASELINE.json `metric` (its throughput clause)
 UNIT = "Gvoxel*iter/s"
 MU = [1.0, 1.0, 0.5, 0.5]
 SHAPE_1GPU = (256, 256, 128, 128)            # BASELINE config 3

@@ -12,7 +12,7 @@ def test_reference_arm_json_line():
                          check=True, capture_output=True, text=True, cwd=ROOT, timeout=600).stdout.strip().splitlines()
     assert len(out) == 1
     d = json.loads(out[0])
-    assert d["impl"] == "reference" and d["metric"] == "tv4d_fista_gvoxel_iter_per_s" and d["unit"] == "Gvoxel*iter/s"
+    assert d["impl"] == "reference" and d["metric"] == "4D TV-FISTA Gvoxel-iter/s" and d["unit"] == "Gvoxel*iter/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
