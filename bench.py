@@ -23,8 +23,11 @@ from __future__ import annotations
 
 import os
 
-# all host cores for the reference's OpenMP kernels (must be set before libgomp is loaded)
-os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+# All host cores for the reference's OpenMP kernels.  Must happen before libgomp is loaded, and must OVERRIDE the
+# environment: torchrun exports OMP_NUM_THREADS=1 to every rank, which made round 1's N>1 reference arm single
+# threaded.  Only rank 0 ever runs CPU legs.  CYTVDN_BENCH_OMP_THREADS pins another count.
+if os.environ.get("RANK", "0") == "0":
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("CYTVDN_BENCH_OMP_THREADS", str(os.cpu_count() or 1))
 
 import argparse
 import json
@@ -121,9 +124,22 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, budget_s=25.0):
-    """4-D FISTA iterations of the reference's CPU implementation on CPU_SAMPLE_SHAPE.
-    Returns dict(value, ms_per_step, steps, kind, cores, sample)."""
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1048576.0
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_reference_run(steps, warmup, budget_s=25.0, full_size=False):
+    """4-D FISTA iterations of the reference's CPU implementation (its unmodified kernels from oracle/_ref, driven
+    as cyTVDN.py:154-184 drives them; the C port when oracle/_ref is absent).  ``full_size``: the config-3 array
+    itself when the host has the memory for the reference's 10 arrays (43 GB), else -- and for the bounded
+    cpu_baseline leg of the GPU arm -- CPU_SAMPLE_SHAPE, same generator, reduced scan size.
+    Returns dict(value, ms_per_step, steps, warmup, kind, cores, sample, shape)."""
     from oracle import tv_oracle as O
     from cytvdn_b200 import synth
     kind = "reference" if O.reference_available() else "port"
@@ -131,9 +147,14 @@ def cpu_reference_run(steps, warmup, budget_s=25.0):
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     if kind == "port":
         O.set_threads(cores)
-    shape = CPU_SAMPLE_SHAPE
-    data = synth.stem4d_hash_numpy(shape, seed=2, counts=500.0)
-    t = data.dtype.type
+    data = synth.stem4d_hash_numpy(CPU_SAMPLE_SHAPE, seed=2, counts=500.0)
+    shape, how = CPU_SAMPLE_SHAPE, "same generator, reduced scan size"
+    if full_size and mem_available_gb() >= 60.0:
+        # the full 256x256x128x128 array: the sample block repeated over the scan axes (generating 1.07 G voxels
+        # with the NumPy mirror of the device generator would take minutes; per-voxel cost does not depend on it)
+        reps = (SHAPE_1GPU[0] // shape[0], SHAPE_1GPU[1] // shape[1], 1, 1)
+        data = np.tile(data, reps)
+        shape, how = SHAPE_1GPU, "full config-3 size, the 32x32 scan sample tiled 8x8"
     mu = np.array(MU, dtype=np.float32)
     lam = mu / 32.0
     clip, w = 1.0 / lam, (lam / mu).astype(np.float32)
@@ -151,33 +172,38 @@ def cpu_reference_run(steps, warmup, budget_s=25.0):
             K.accumulator_update(recon, acc[ax], dd[ax], r, ax, clip[ax], 2)
         K.datacube_update(data, recon, acc, w, 2)
 
+    # warm-up (the first iteration also first-touches the arrays and calibrates the budget)
     t0 = time.perf_counter()
-    one()                                            # calibration (also first-touch of the arrays)
+    one()
     t_one = time.perf_counter() - t0
-    w_eff = max(0, min(warmup, int(0.25 * budget_s / max(t_one, 1e-6)) - 1))
-    k_eff = max(1, min(steps, int(0.75 * budget_s / max(t_one, 1e-6))))
-    for _ in range(w_eff):
+    w_eff = max(1, min(warmup, int(0.25 * budget_s / max(t_one, 1e-6))))
+    for _ in range(w_eff - 1):
         one()
+    k_eff = max(1, min(steps, int(0.75 * budget_s / max(t_one, 1e-6))))
     t0 = time.perf_counter()
     for _ in range(k_eff):
         one()
     dt = time.perf_counter() - t0
-    return dict(value=vox * k_eff / dt / 1e9, ms_per_step=1e3 * dt / k_eff, steps=k_eff, warmup=w_eff + 1,
-                kind=kind, cores=cores,
-                sample=f"4-D FISTA fp32 {'x'.join(map(str, shape))} (same generator, reduced scan size), "
-                       f"{k_eff} timed iterations after {w_eff + 1} warm-up, OMP_NUM_THREADS={cores}")
+    return dict(value=vox * k_eff / dt / 1e9, ms_per_step=1e3 * dt / k_eff, steps=k_eff, warmup=w_eff,
+                kind=kind, cores=cores, shape=list(shape),
+                sample=f"4-D FISTA fp32 {'x'.join(map(str, shape))} ({how}), "
+                       f"{k_eff} timed iterations after {w_eff} warm-up, OMP_NUM_THREADS={cores}")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference_run(args.steps, args.warmup, budget_s=60.0)
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=150.0, full_size=True)
+    cfg = workload_config(args.gpus)
+    cfg["cpu_sample_shape"] = r["shape"]
+    cfg["cpu_sample"] = ("the reference's CPU path cannot hold the sharded arrays; each step is one FISTA iteration over "
+                         + "x".join(map(str, r["shape"])) + " voxels of the same workload, reported per voxel")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,7 +238,7 @@ def run_single(args):
     torch.cuda.set_device(0)
     shape = tuple(args.shape) if args.shape else SHAPE_1GPU
     vox = int(np.prod(shape))
-    fused = args.schedule in ("fused", "peer")       # "peer" only differs in how shards talk; one GPU has no peers
+    fused = args.schedule != "two_pass"              # the other names only differ in how shards talk to each other
     x = synth.stem4d_device(shape, seed=2, counts=500.0)
     nset = 2 if fused else 1
     # --skew: offset the k-th state array by k * SKEW bytes (experiment: power-of-two array sizes showed no
@@ -292,7 +318,7 @@ def run_single(args):
     s_host = sums.cpu().numpy().reshape(-1, 4)
     last = s_host[state["it"] - 1]
     peak, peak_src = measured_peak()
-    traffic = committed_traffic()
+    traffic = committed_traffic() if shape == SHAPE_1GPU else {}        # the ncu capture is of config 3
     eq96 = (BYTES_A + BYTES_B) * vox / (ms_per_step * 1e-3) / 1e9
     if fused:
         # a fused single pass is still reported against the 96 B/voxel contract figure of
@@ -325,29 +351,56 @@ def run_single(args):
     torch.cuda.empty_cache()
 
     # ---- end to end through the public API with pinned host buffers ------------------------------
+    # tv.denoise4D(host array in, host array out): H2D of the data and D2H of the result inside every timed call.
+    # The device working set is reserved once (tv.workspace_reserve, the C ABI's cytvdn_workspace_reserve), as a
+    # caller that denoises more than one cube would do, so cudaMalloc/cudaFree of ~86 GB (60 ms .. 0.7 s, the
+    # unexplained host time of round 1) are not part of a call; >= 3 timed calls, all samples reported, value = median.
     e2e = None
     if not args.no_e2e:
         iters = args.e2e_iters
+        sched = "fused" if fused else "two_pass"
         host_in = tv.pinned_empty(shape, np.float32)
         host_out = tv.pinned_empty(shape, np.float32)
         torch.from_numpy(host_in).copy_(x)
         del x
         torch.cuda.empty_cache()
         torch.cuda.synchronize()
+        reserved = tv.workspace_reserve((shape, np.float32), iterations=iters, FISTA=True, host_arrays=True, schedule=sched)
         # one short untimed call first (same arrays, 3 iterations): first-use costs of the copy path
-        tv.denoise4D(host_in, mu, iterations=3, FISTA=True, quiet=True, out=host_out,
-                     schedule="fused" if fused else "two_pass")
-        tm = {}
-        t0 = time.perf_counter()
-        tv.denoise4D(host_in, mu, iterations=iters, FISTA=True, quiet=True, out=host_out, timing=tm,
-                     schedule="fused" if fused else "two_pass")
-        dt = time.perf_counter() - t0
+        tv.denoise4D(host_in, mu, iterations=3, FISTA=True, quiet=True, out=host_out, schedule=sched)
+        samples, tms = [], []
+        for _ in range(max(1, args.e2e_calls)):
+            tm = {}
+            t0 = time.perf_counter()
+            tv.denoise4D(host_in, mu, iterations=iters, FISTA=True, quiet=True, out=host_out, timing=tm, schedule=sched)
+            samples.append(time.perf_counter() - t0)
+            tms.append(tm)
+        tv.workspace_release()
+        order = np.argsort(samples)
+        mid = int(order[len(order) // 2])
+        dt, tm = samples[mid], tms[mid]
         nbytes = vox * 4
         e2e = {"value": vox * iters / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes / iters,
                "d2h_bytes_per_step": nbytes / iters,
-               "call": f"tv.denoise4D(pinned host fp32, iterations={iters}, FISTA=True, schedule={tm.get('schedule')})",
-               "wall_s": dt, "warmup_calls": 1, "pcie_pipeline_boxes": tm.get("pipeline_boxes"), "setup_ms": tm.get("setup_ms"), "loop_ms": tm.get("loop_ms"), "finish_ms": tm.get("finish_ms"),
+               "call": f"tv.denoise4D(pinned host fp32, iterations={iters}, FISTA=True, schedule={tm.get('schedule')}), "
+                       f"device working set reserved once with tv.workspace_reserve ({reserved / 2**30:.1f} GiB)",
+               "wall_s": dt, "wall_s_samples": samples,
+               "value_samples": [vox * iters / t / 1e9 for t in samples], "timed_calls": len(samples),
+               "spread": (max(samples) - min(samples)) / dt,
+               "warmup_calls": 1, "pcie_pipeline_boxes": tm.get("pipeline_boxes"), "setup_ms": tm.get("setup_ms"),
+               "loop_ms": tm.get("loop_ms"), "finish_ms": tm.get("finish_ms"), "trace_ms": tm.get("trace_ms"),
                "h2d_bytes_total": nbytes, "d2h_bytes_total": nbytes}
+        del host_in, host_out
+    else:
+        del x
+    torch.cuda.empty_cache()
+    configs = None
+    if args.configs and not args.shape:
+        try:
+            from bench_configs import run_configs
+            configs = run_configs(peak)
+        except Exception as ex:           # a side key must never take the headline line down
+            configs = {"error": repr(ex)[:300]}
     cpu = None
     if not args.no_cpu:
         r = cpu_reference_run(5, 1, budget_s=20.0)
@@ -360,6 +413,7 @@ def run_single(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "configs": configs,
             "check": {"bnorm_last": float(last[0]), "delta_last": float(last[1] / last[2]) if last[2] else None}}
     print(json.dumps(line), flush=True)
     return 0
@@ -373,11 +427,20 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shape", type=int, nargs=4, default=None, help="override the N=1 shape (debugging)")
     ap.add_argument("--e2e-iters", type=int, default=100)
+    ap.add_argument("--e2e-calls", type=int, default=3, help="timed end-to-end calls (median reported)")
+    ap.add_argument("--no-configs", dest="configs", action="store_false",
+                    help="skip the `configs` extra key (C1, C2, C4, unaccelerated, fp64 through the public API)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--skew", type=int, default=0, help="byte skew between consecutive state arrays (experiment knob)")
-    ap.add_argument("--schedule", default="fused", choices=["fused", "two_pass", "peer"],
-                    help="fused: one pass per iteration (76 B/voxel); two_pass: half-steps A and B (96 B/voxel)")
+    ap.add_argument("--schedule", default="fused", choices=["fused", "two_pass", "peer", "engine", "nccl_fused"],
+                    help="fused: one pass per iteration (76 B/voxel; N > 1: the C-ABI shard engine, copy-engine halo "
+                         "exchange); two_pass: half-steps A and B (96 B/voxel; N > 1: NCCL exchange); nccl_fused / peer: "
+                         "round 1's torch.distributed schedules (N > 1)")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the parity checks over the process group")
+    ap.add_argument("--no-alone", action="store_true", help="N > 1: skip the single-GPU run of one shard's shape")
+    ap.add_argument("--timeline", default=None, help="N > 1: write per-phase CUDA-event timings of the timed steps here")
+    ap.add_argument("--timeline-full", action="store_true", help="keep every iteration of every rank in the timeline file")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

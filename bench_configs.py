@@ -1,0 +1,109 @@
+"""bench.py's ``configs`` extra key: every BASELINE.json config that fits one GPU (C1, C2 fixed-100 and
+stopping_relative_change=0.05, C4, plus the 4-D unaccelerated and float64 variants), each through the PUBLIC API
+``tv.denoise3D`` / ``tv.denoise4D``:
+
+  value  -- Gvoxel*iter/s of the iteration loop on a device-resident tensor (the library's CUDA events);
+  frac   -- that rate x the SURVEY 8d contract bytes/voxel (two-pass figure) / measured HBM copy peak, and
+            moved_frac with the bytes the schedule that ran really moves;
+  e2e    -- the same call with pinned HOST arrays in and out (copies inside the timed wall clock).
+
+The headline line of bench.py stays config 3; these entries are context the round-1 review asked to see in the
+driver's own record instead of in builder-run files.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+
+def _bytes_per_voxel(ndim, fista, fused, elem):
+    """Algorithmic bytes per voxel and iteration: DESIGN.md section 4 (fused: every array once; two-pass: SURVEY 8d)."""
+    if fused:
+        return (3 + ndim * (4 if fista else 2)) * elem
+    return (1 + ndim * (4 if fista else 2) + 2 + ndim + 1) * elem
+
+
+def run_configs(peak_gbs, quick=False):
+    import torch
+    import cytvdn_b200 as tv
+    from cytvdn_b200 import synth
+
+    out = []
+    f32 = np.float32
+
+    def one(name, fn, dev_data, mu, ndim, fista, iters, e2e=True, **kw):
+        elem = dev_data.element_size()
+        nvox = dev_data.numel()
+        rec = {"config": name, "shape": list(dev_data.shape), "dtype": "f32" if elem == 4 else "f64"}
+        tm = {}
+        fn(dev_data, mu, quiet=True, timing=tm, **dict(kw, iterations=3))                    # warm-up
+        tm = {}
+        r = fn(dev_data, mu, quiet=True, timing=tm, **dict(kw, iterations=iters))
+        done = tm["iters_fista"] + tm["iters_plain"]
+        fused = tm["schedule"] == "fused"
+        gv = nvox * done / (tm["loop_ms"] * 1e-3) / 1e9
+        contract = _bytes_per_voxel(ndim, fista, False, elem)
+        moved = _bytes_per_voxel(ndim, fista, fused, elem)
+        rec.update(value=gv, unit="Gvoxel*iter/s", iterations_run=done, ms_per_iter=tm["loop_ms"] / max(done, 1),
+                   schedule=tm["schedule"], contract_bytes_per_voxel=contract, frac=gv * contract / peak_gbs,
+                   moved_bytes_per_voxel=moved, moved_frac=gv * moved / peak_gbs,
+                   delta_last=float(r[2][done - 1]) if done else None)
+        del r
+        torch.cuda.empty_cache()
+        if e2e:
+            dt_np = f32 if elem == 4 else np.float64
+            host_in = tv.pinned_empty(tuple(dev_data.shape), dt_np)
+            host_out = tv.pinned_empty(tuple(dev_data.shape), dt_np)
+            torch.from_numpy(host_in).copy_(dev_data)
+            torch.cuda.synchronize()
+            mu_h = np.asarray(mu)
+            fn(host_in, mu_h, quiet=True, out=host_out, **dict(kw, iterations=3))
+            tm = {}
+            t0 = time.perf_counter()
+            fn(host_in, mu_h, quiet=True, out=host_out, timing=tm, **dict(kw, iterations=iters))
+            dt = time.perf_counter() - t0
+            done_h = tm["iters_fista"] + tm["iters_plain"]
+            rec["e2e"] = {"value": nvox * done_h / dt / 1e9, "unit": "Gvoxel*iter/s", "wall_s": dt,
+                          "iterations_run": done_h, "h2d_bytes": nvox * elem, "d2h_bytes": nvox * elem,
+                          "schedule": tm["schedule"], "pcie_pipeline_boxes": tm.get("pipeline_boxes")}
+            del host_in, host_out
+        out.append(rec)
+        return rec
+
+    mu3 = np.array([1, 1, .5], dtype=f32)
+    mu4 = np.array([1, 1, .5, .5], dtype=f32)
+    # ---- C1: denoise3D anisotropic unaccelerated, 128x128x1024, 100 iterations ------------------------------
+    cube = torch.from_numpy(synth.eels_cube((128, 128, 1024), seed=0, dose=1000.0, gain=1.0)).cuda()
+    one("C1 denoise3D plain 128x128x1024, 100 it.", tv.denoise3D, cube, mu3, 3, False, 100, FISTA=False)
+    del cube
+    # ---- C2: denoise3D FISTA 512x512x2048 (EELS-like cube built on the device: a host Poisson draw of 0.5 G
+    #      voxels takes minutes), fixed 100 iterations and stopping_relative_change=0.05 -----------------------
+    if not quick:
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(1)
+        clean = synth.eels_clean((512, 512, 2048), dose=2.0)                                 # noise-free profile, dose 2
+        big = torch.poisson(torch.from_numpy(clean).cuda(), generator=gen).mul_(8.0)         # gain 8
+        del clean
+        one("C2 denoise3D FISTA 512x512x2048, fixed 100 it.", tv.denoise3D, big, mu3, 3, True, 100, FISTA=True)
+        one("C2 denoise3D FISTA 512x512x2048, stopping_relative_change=0.05", tv.denoise3D, big, mu3, 3, True, 100,
+            FISTA=True, stopping_relative_change=0.05)
+        del big
+        torch.cuda.empty_cache()
+    # ---- C4 (half-isotropic), 4-D unaccelerated: 256x256x128x128 ------------------------------------------------
+    shape4 = (64, 64, 128, 128) if quick else (256, 256, 128, 128)
+    x = synth.stem4d_device(shape4, seed=2, counts=500.0)
+    one(f"C4 denoise4D half-isotropic FISTA {'x'.join(map(str, shape4))}, 100 it.", tv.denoise4D, x, mu4, 4, True, 100,
+        FISTA=True, isotropic_R=True, isotropic_Q=True)
+    one(f"denoise4D anisotropic unaccelerated {'x'.join(map(str, shape4))}, 100 it.", tv.denoise4D, x, mu4, 4, False, 100,
+        e2e=False, FISTA=False)
+    del x
+    torch.cuda.empty_cache()
+    # ---- float64 ------------------------------------------------------------------------------------------------
+    shape64 = (32, 64, 128, 128) if quick else (128, 256, 128, 128)
+    x64 = synth.stem4d_device(shape64, seed=2, counts=500.0, dtype="float64")
+    one(f"fp64 denoise4D anisotropic FISTA {'x'.join(map(str, shape64))}, 50 it.", tv.denoise4D, x64,
+        mu4.astype(np.float64), 4, True, 50, e2e=False, FISTA=True)
+    del x64
+    torch.cuda.empty_cache()
+    return out

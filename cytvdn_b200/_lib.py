@@ -38,6 +38,23 @@ class StepOpts(C.Structure):
     ]
 
 
+class ShardParams(C.Structure):
+    """``cytvdn_shard_params`` (include/cytvdn_b200.h)."""
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("periodic", C.c_int32),
+        ("fista", C.c_int32),
+        ("max_iters", C.c_int32),
+        ("device", C.c_int32),
+        ("reserved", C.c_int32),
+        ("gshape", C.c_int64 * 4),
+        ("clip", C.c_double * 4),
+        ("lambda_mu", C.c_double * 4),
+    ]
+
+
 class DenoiseParams(C.Structure):
     """``cytvdn_denoise_params`` (include/cytvdn_b200.h)."""
     _fields_ = [
@@ -81,6 +98,28 @@ PROTOTYPES = {
     "cytvdn_denoise": (C.c_int, [C.POINTER(DenoiseParams), _vp, _vp, _vp, _dp, _dp, _dp,
                                  C.POINTER(C.c_int32), _dp]),
     "cytvdn_denoise_workspace_bytes": (C.c_int, [C.POINTER(DenoiseParams), C.c_int, C.c_int, _i64p]),
+    "cytvdn_workspace_reserve": (C.c_int, [C.c_int64]),
+    "cytvdn_workspace_release": (C.c_int, []),
+    "cytvdn_workspace_info": (C.c_int, [_i64p, _i64p]),
+    "cytvdn_last_trace": (C.c_int, [_dp, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_int)]),
+    "cytvdn_shard_create": (C.c_int, [C.POINTER(ShardParams), _vpp]),
+    "cytvdn_shard_destroy": (C.c_int, [_vp]),
+    "cytvdn_shard_info": (C.c_int, [_vp, _i64p]),
+    "cytvdn_shard_export": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
+    "cytvdn_shard_connect": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_ubyte)]),
+    "cytvdn_shard_load": (C.c_int, [_vp, _vp]),
+    "cytvdn_shard_iterate": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "cytvdn_shard_synchronize": (C.c_int, [_vp]),
+    "cytvdn_shard_sums": (C.c_int, [_vp, _dp, C.c_int]),
+    "cytvdn_shard_store": (C.c_int, [_vp, _vp]),
+    "cytvdn_shard_array": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vpp]),
+    "cytvdn_shard_streams": (C.c_int, [_vp, _vpp, _vpp]),
+    "cytvdn_shard_profile": (C.c_int, [_vp, C.c_int]),
+    "cytvdn_shard_timeline": (C.c_int, [_vp, _dp, C.c_int]),
+    "cytvdn_denoise_sharded": (C.c_int, [C.POINTER(DenoiseParams), C.c_int, C.POINTER(C.c_int), _vp, _vp, _dp, _dp,
+                                         C.POINTER(C.c_int32), _dp]),
+    "cytvdn_denoise_sharded_streamed": (C.c_int, [C.POINTER(DenoiseParams), C.c_int, C.POINTER(C.c_int), _vp, _vp, _dp,
+                                                  _dp, C.POINTER(C.c_int32), _dp]),
     "cytvdn_pipeline_schedule": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64, _i64p]),
     "cytvdn_stream_plan": (C.c_int, [C.POINTER(DenoiseParams), C.c_int64, _i64p]),
     "cytvdn_synth_counts": (C.c_int, [_i64p, C.c_int64, C.c_int64, C.c_int, _vp, _vp, C.c_double, C.c_uint64,

@@ -54,7 +54,9 @@ def build_parser():
     p.add_argument("--stop", type=float, default=None, help="stopping_relative_change")
     p.add_argument("--grid", default="1d", choices=["1d", "mpi"], help="tile layout: axis-0 split or mpi.py's (wx, wy)")
     p.add_argument("--schedule", default="auto", choices=["auto", "fused", "two_pass", "streamed"],
-                   help="streamed: out of core, one GPU only")
+                   help="streamed: out of core (one process: one GPU, or --devices N)")
+    p.add_argument("--devices", type=int, default=0,
+                   help="without torchrun: shard over this many GPUs from one process (cytvdn_denoise_sharded)")
     return p
 
 
@@ -126,7 +128,21 @@ def main(argv=None):
     say(f"Loaded memory map. Data size is: {tuple(data.shape)}")
     t0 = time.time()
 
-    if world == 1:
+    if world == 1 and args.devices and args.devices > 1:
+        # several GPUs from ONE process (cytvdn_denoise_sharded): host arrays in and out, shards of scan axis 0;
+        # --schedule streamed additionally runs shards that do not fit their GPU out of core
+        if ndim != 4:
+            raise SystemExit("sharded runs exist for 4-D data only (as in the reference, mpi.py:252-255)")
+        block = read_block(data, tuple(slice(None) for _ in range(ndim)))
+        out = create_output(args.output[0], data.shape)
+        tm = {}
+        recon, bn, dl = tv.denoise4D(block, mu, iterations=iterations, FISTA=fista, stopping_relative_change=args.stop,
+                                     lam=lam, quiet=True, out=out, timing=tm, devices=list(range(args.devices)),
+                                     schedule="streamed" if args.schedule == "streamed" else None)
+        out.flush()
+        say(f"{args.devices} devices from one process, schedule: {tm.get('schedule')}")
+        world = args.devices
+    elif world == 1:
         # host arrays in and out: the library overlaps the PCIe copies with the iterations and, when the arrays do
         # not fit in the GPU's memory, iterates them tile by tile (out-of-core schedule); the result is written
         # straight into the memory-mapped output file
@@ -149,15 +165,24 @@ def main(argv=None):
         try:
             plan = sharded.ShardPlan(data.shape, world, rank, None if args.grid == "1d" else "mpi")
             say(f"Dividing work over a {plan.grid[0]} by {plan.grid[1]} grid...")
-            block = torch.from_numpy(read_block(data, plan.read_global)).to(dev)
             if args.schedule == "streamed":
-                raise SystemExit("--schedule streamed runs on one GPU only")
-            recon, bn, dl = sharded.denoise4D_sharded(block, mu, iterations, fista, args.stop, plan=plan, lam=lam,
-                                                      schedule=args.schedule)
+                raise SystemExit("--schedule streamed under torchrun: use one process with --devices N instead "
+                                 "(the out-of-core shards are driven from one process)")
+            if plan.grid[1] == 1 and args.schedule in ("auto", "fused"):
+                # 1-D split: the C-ABI shard engine (copy-engine halo exchange over CUDA IPC); the block goes
+                # host -> device inside the library, the owned planes come back as a host array
+                block = read_block(data, plan.read_global)
+                own, bn, dl = sharded.denoise4D_engine(block, mu, iterations, fista, args.stop, gshape=data.shape, lam=lam)
+                owned = own
+            else:
+                block = torch.from_numpy(read_block(data, plan.read_global)).to(dev)
+                recon, bn, dl = sharded.denoise4D_sharded(block, mu, iterations, fista, args.stop, plan=plan, lam=lam,
+                                                          schedule=args.schedule)
+                owned = recon[plan.owned_local].cpu().numpy()
             if head:
                 create_output(args.output[0], data.shape)
             dist.barrier()
-            write_block(args.output[0], plan.owned_global, recon[plan.owned_local].cpu().numpy())
+            write_block(args.output[0], plan.owned_global, owned)
             dist.barrier()
         finally:
             dist.destroy_process_group()

@@ -53,6 +53,7 @@ struct Sweep {
     int32_t ntiles;
     int32_t oi0, oi1, oj0, oj1;// voxels with i in [oi0,oi1) and j in [oj0,oj1) enter the reductions
     int32_t dynamic;           // 1: tiles are drawn from a global counter, 0: static stride gridDim.x
+    int32_t own_store;         // 1: the fused kernels store recon_out only for voxels inside the owned range
     FastDiv d_tiles_full, d_cps_full, d_cps_last, d_mv, d_n3v;
 };
 

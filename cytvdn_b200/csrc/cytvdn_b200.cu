@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include "fused.cuh"
 #include "fused_tma.cuh"
+#include "internal.hh"
 
 #include <sys/mman.h>
 
@@ -51,13 +52,29 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 // ---- per (device, stream) reduction workspace ----------------------------------------------
+// One small scratch block (per-CTA partial sums + ticket) per (device, stream) pair that has launched a reducing
+// kernel: launches on one stream are serialised, launches on different streams may overlap and must not share the
+// ticket.  The table is bounded: beyond kMaxWorkspaces entries the least recently used one is freed (cudaFree
+// synchronises the device, so a workspace is never freed under a running kernel), and
+// cytvdn_workspace_release() drops all of them.  A stream handle the runtime recycles for a new stream simply
+// finds the old stream's block (the ticket is zero between launches), which is harmless.
 struct Workspace {
     double *partials = nullptr;   // [kMaxGrid][4]
     unsigned *ticket = nullptr;
+    uint64_t stamp = 0;           // last use (LRU)
 };
 constexpr int kMaxGrid = 148 * 16;
+constexpr size_t kMaxWorkspaces = 64;
 std::mutex g_ws_mutex;
 std::map<std::pair<int, cudaStream_t>, Workspace> g_ws;
+uint64_t g_ws_clock = 0;
+
+void free_workspace(Workspace &w)
+{
+    if (w.partials) cudaFree(w.partials);
+    if (w.ticket) cudaFree(w.ticket);
+    w.partials = nullptr; w.ticket = nullptr;
+}
 
 int get_workspace(cudaStream_t st, Workspace *out)
 {
@@ -67,14 +84,31 @@ int get_workspace(cudaStream_t st, Workspace *out)
     auto key = std::make_pair(dev, st);
     auto it = g_ws.find(key);
     if (it == g_ws.end()) {
+        if (g_ws.size() >= kMaxWorkspaces) {            // evict the least recently used block of THIS device
+            auto victim = g_ws.end();
+            for (auto j = g_ws.begin(); j != g_ws.end(); ++j)
+                if (j->first.first == dev && (victim == g_ws.end() || j->second.stamp < victim->second.stamp)) victim = j;
+            if (victim != g_ws.end()) { free_workspace(victim->second); g_ws.erase(victim); }
+        }
         Workspace w;
         CUDA_TRY(cudaMalloc(&w.partials, sizeof(double) * 4 * kMaxGrid));
         CUDA_TRY(cudaMalloc(&w.ticket, sizeof(unsigned) * 4));
         CUDA_TRY(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned) * 4, st));
         it = g_ws.emplace(key, w).first;
     }
+    it->second.stamp = ++g_ws_clock;
     *out = it->second;
     return CYTVDN_OK;
+}
+
+// drop every reduction workspace of device `dev` (the caller has synchronised it)
+void drop_workspaces(int dev)
+{
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    for (auto it = g_ws.begin(); it != g_ws.end();) {
+        if (it->first.first == dev) { free_workspace(it->second); it = g_ws.erase(it); }
+        else ++it;
+    }
 }
 
 // ---- device properties / occupancy cache ------------------------------------------------------
@@ -203,6 +237,7 @@ int make_sweep(const Dims &D, int vw, size_t elem, const cytvdn_step_opts *o, in
         }
     }
     S->dynamic = (o && (o->flags & 1)) ? 1 : 0;
+    S->own_store = (o && (o->flags & 2)) ? 1 : 0;
     S->i0 = (int32_t)lo[0]; S->ni = (int32_t)(hi[0] - lo[0]);
     S->j0 = (int32_t)lo[1];
     const int64_t nj = hi[1] - lo[1];
@@ -434,6 +469,7 @@ struct FusedCall {
     double clip[4], w[4];
     int bc[4];
     bool fista;
+    int iso_mask;                                // bit 0: pair (0,1), bit 1: pair (2,3) half-isotropic
     double tk;
     int zero_wrap;
     double *sums_dev;
@@ -493,6 +529,29 @@ int run_fused(const FusedCall &c)
         if (c.fista) { if (ax2) LAUNCH_TMA(true, true); else LAUNCH_TMA(true, false); }
         else         { if (ax2) LAUNCH_TMA(false, true); else LAUNCH_TMA(false, false); }
 #undef LAUNCH_TMA
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+        return CYTVDN_OK;
+    }
+    if (c.iso_mask) {
+        // half-isotropic pairs: 4-D, full vector width (cytvdn_denoise and the sharded drivers pad rows to it)
+        if (!ax2 || !vec)
+            return fail(CYTVDN_E_UNSUPPORTED, "the fused half-isotropic iteration needs a 4-D array whose rows are 16-byte "
+                                              "aligned (row length or cytvdn_step_opts.row_pitch a multiple of %d elements)",
+                        vec_width<T>());
+        if (c.lo_u || c.hi_u) return fail(CYTVDN_E_UNSUPPORTED, "peer pointers are not supported with half-isotropic pairs");
+        auto go = [&](auto k) -> int {
+            if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
+            k<<<grid, kBlock, 0, c.st>>>(P);
+            return CYTVDN_OK;
+        };
+        int rc = CYTVDN_OK;
+        const bool R = c.iso_mask & 1, Q = c.iso_mask & 2;
+        if (c.fista) rc = R ? (Q ? go(tv_fused_iso_kernel<T, true, true, true>) : go(tv_fused_iso_kernel<T, true, true, false>))
+                            : go(tv_fused_iso_kernel<T, true, false, true>);
+        else rc = R ? (Q ? go(tv_fused_iso_kernel<T, false, true, true>) : go(tv_fused_iso_kernel<T, false, true, false>))
+                    : go(tv_fused_iso_kernel<T, false, false, true>);
+        if (rc) return rc;
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
         return CYTVDN_OK;
@@ -650,12 +709,15 @@ int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void
     if (bc_mode == 3)
         return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=3 (clamped mirror) runs on the two-pass schedule only");
     if (bc_mode != 0 && bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
+    c.iso_mask = opts ? ((opts->flags >> 4) & 3) : 0;
+    if (c.iso_mask && ndim != 4) return fail(CYTVDN_E_INVALID, "half-isotropic update exists for 4-D only");
     for (int k = 0; k < ndim; ++k) {
         const int s = c.D.axmap[k];
         c.bin[s] = b_in[k]; c.bout[s] = b_out[k];
         c.din[s] = d_in ? d_in[k] : nullptr; c.dout[s] = d_out ? d_out[k] : nullptr;
         c.clip[s] = clip[k]; c.w[s] = lambda_mu[k];
-        c.bc[s] = (opts && ((opts->flags >> (8 + k)) & 1)) ? 2 : bc_mode;
+        const bool iso = (k < 2 && (c.iso_mask & 1)) || (k >= 2 && (c.iso_mask & 2));   // iso_* kernels know Jia-Zhao only
+        c.bc[s] = (iso || (opts && ((opts->flags >> (8 + k)) & 1))) ? 2 : bc_mode;
         if (opts && ((opts->zero_wrap_mask >> k) & 1)) c.zero_wrap |= 1 << s;
     }
     c.orig = orig; c.uin = recon_in; c.uout = recon_out;
@@ -734,7 +796,7 @@ namespace {
 // 1 = two passes (96 B/voxel, in place).  params->schedule: 0 auto, 1, 2; env CYTVDN_SCHEDULE overrides.
 bool fused_possible(const cytvdn_denoise_params *p)
 {
-    return !p->isotropic_R && !p->isotropic_Q && (p->bc_mode == 0 || p->bc_mode == 2);
+    return p->bc_mode == 0 || p->bc_mode == 2;      // anisotropic and half-isotropic; the mirror (3) runs two-pass
 }
 int requested_schedule(const cytvdn_denoise_params *p)
 {
@@ -770,22 +832,60 @@ int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *p, int data_on_d
     const int64_t elem = p->dtype == CYTVDN_F32 ? 4 : 8, vwf = 16 / elem;
     const bool padded = D.n[3] % vwf != 0;             // internal rows are padded: caller arrays are always copied
     const int64_t nb = D.n[0] * D.n[1] * D.n[2] * ((D.n[3] + vwf - 1) / vwf * vwf) * elem;
-    const bool fused = fused_possible(p) && requested_schedule(p) != 1;
-    *bytes = arrays_needed(p, fused, data_on_device != 0 && !padded, recon_on_device != 0 && !padded, false) * nb;
+    const bool fused = fused_possible(p) && requested_schedule(p) != 1 && (requested_schedule(p) == 2 || !p->isotropic_R);
+    const int64_t nbp = (int64_t)((nb + 255) & ~(int64_t)255);
+    const int64_t scratch = (((int64_t)(p->iters_fista + p->iters_plain + 1) * 4 * 16 * 8 + 255) & ~(int64_t)255) + 8192;
+    *bytes = arrays_needed(p, fused, data_on_device != 0 && !padded, recon_on_device != 0 && !padded, false) * nbp + scratch;
     return CYTVDN_OK;
 }
 
 namespace {
 // All device state of one cytvdn_denoise call lives in ONE allocation that is carved up: on B200 twenty
-// 4 GiB cudaMalloc/cudaFree pairs cost ~250 ms, one 80 GiB pair ~35 ms (tools/alloc_timing.py).
+// 4 GiB cudaMalloc/cudaFree pairs cost ~250 ms, one 80 GiB pair ~35 ms (tools/alloc_timing.py) -- and now and then
+// several hundred ms (round 1: 0.66 s of a 2.1 s call).  A caller that denoises more than once can take even that
+// out of its calls: cytvdn_workspace_reserve() makes the library hold one device block per device, and every Arena
+// whose request fits carves from it instead of calling cudaMalloc (bump allocation, reset when the last borrower
+// returns).  Nothing is ever cached behind the caller's back: without a reservation each call allocates and frees.
+struct Reserved {
+    char *base = nullptr;
+    size_t size = 0, used = 0;
+    int refs = 0;
+};
+std::mutex g_res_mutex;
+std::map<int, Reserved> g_reserved;                       // device -> block held for the caller
+
 struct Arena {
     char *base = nullptr;
     size_t size = 0, used = 0;
+    int borrowed_dev = -1;                                // >= 0: carved from the reserved block of that device
     ~Arena() { release(); }
-    void release() { if (base) cudaFree(base); base = nullptr; size = used = 0; }
+    void release()
+    {
+        if (base && borrowed_dev >= 0) {
+            std::lock_guard<std::mutex> lk(g_res_mutex);
+            auto it = g_reserved.find(borrowed_dev);
+            if (it != g_reserved.end() && --it->second.refs == 0) it->second.used = 0;
+        } else if (base) {
+            cudaFree(base);
+        }
+        base = nullptr; size = used = 0; borrowed_dev = -1;
+    }
     static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
     int reserve(size_t bytes)
     {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(g_res_mutex);
+            auto it = g_reserved.find(dev);
+            const size_t need = padded(bytes);
+            if (it != g_reserved.end() && it->second.base && it->second.used + need <= it->second.size) {
+                base = it->second.base + it->second.used;
+                it->second.used += need;
+                ++it->second.refs;
+                size = bytes; borrowed_dev = dev;
+                return CYTVDN_OK;
+            }
+        }
         cudaError_t e = cudaMalloc((void **)&base, bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -804,6 +904,26 @@ struct Arena {
         return CYTVDN_OK;
     }
 };
+
+// host-clock milestones of the calling thread's last cytvdn_denoise (cytvdn_last_trace)
+constexpr int kTraceMax = 12;
+thread_local double g_trace_ms[kTraceMax];
+thread_local const char *g_trace_what[kTraceMax];
+thread_local int g_trace_n = 0;
+
+// device memory a call can count on: what the driver reports free plus the unused part of the caller's reservation
+int available_bytes(size_t *out)
+{
+    size_t free_b = 0, tot_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_res_mutex);
+    auto it = g_reserved.find(dev);
+    if (it != g_reserved.end() && it->second.base) free_b += it->second.size - it->second.used;
+    *out = free_b;
+    return CYTVDN_OK;
+}
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1234,9 +1354,11 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     // CYTVDN_TRACE=1: host-clock milestones of the call on stderr (where the wall time outside the CUDA events goes)
     const bool trace = [] { const char *e = getenv("CYTVDN_TRACE"); return e && *e && strcmp(e, "0"); }();
     const auto t_start = std::chrono::steady_clock::now();
+    g_trace_n = 0;
     auto mark = [&](const char *what) {
-        if (trace) fprintf(stderr, "[cytvdn_denoise] %8.2f ms  %s\n",
-                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+        if (g_trace_n < kTraceMax) { g_trace_ms[g_trace_n] = ms; g_trace_what[g_trace_n] = what; ++g_trace_n; }
+        if (trace) fprintf(stderr, "[cytvdn_denoise] %8.2f ms  %s\n", ms, what);
     };
     if (data == recon) return fail(CYTVDN_E_INVALID, "recon must not alias data (the input is read in every iteration)");
     const int nF = p->iters_fista, nU = p->iters_plain, nIt = nF + nU;
@@ -1257,12 +1379,15 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     cytvdn_step_opts sopts;
     memset(&sopts, 0, sizeof sopts);
     sopts.row_pitch = n3p;
+    sopts.flags = (p->isotropic_R ? 16 : 0) | (p->isotropic_Q ? 32 : 0);     // read by the fused iteration only
 
-    const bool data_dev = is_device_ptr(data) && !padded, recon_dev = is_device_ptr(recon) && !padded;
+    // residency of the caller's arrays (decides which schedules apply) vs "can be used in place" (dense rows only)
+    const bool data_on_dev = is_device_ptr(data), recon_on_dev = is_device_ptr(recon);
+    const bool data_dev = data_on_dev && !padded, recon_dev = recon_on_dev && !padded;
     const bool ref_dev = reference_data ? (is_device_ptr(reference_data) && !padded) : false;
     int prev_dev = -1;
     CUDA_TRY(cudaGetDevice(&prev_dev));
-    if (!data_dev && p->device >= 0) CUDA_TRY(cudaSetDevice(p->device));
+    if (!data_on_dev && p->device >= 0) CUDA_TRY(cudaSetDevice(p->device));
     struct Restore {
         int d;
         void now() { int c = -1; if (d >= 0 && (cudaGetDevice(&c) != cudaSuccess || c != d)) cudaSetDevice(d); d = -1; }
@@ -1275,9 +1400,10 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         bool want = requested_schedule(p) == 3;
         size_t budget = 0;
         { const char *env = getenv("CYTVDN_STREAM_BUDGET_MB"); if (env && atof(env) > 0) { budget = (size_t)(atof(env) * 1048576.0); want = true; } }
-        const bool can = !data_dev && !recon_dev && p->bc_mode == 2 && !p->use_stopping && !reference_data && nIt > 0;
-        size_t free_b = 0, tot_b = 0;
-        if (can || want) CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+        const bool can = !data_on_dev && !recon_on_dev && p->bc_mode == 2 && !p->use_stopping && !reference_data && nIt > 0;
+        size_t free_b = 0;
+        // (cudaMemGetInfo costs 15 - 20 ms on a B200 with tens of GB allocated: asked only when the answer matters)
+        if (want || (can && requested_schedule(p) == 0)) if (int rc = available_bytes(&free_b)) return rc;
         if (!want && can && requested_schedule(p) == 0) {
             const int64_t in_core = arrays_needed(p, false, false, false, false) * (int64_t)nb;     // two-pass, in place
             want = in_core + (int64_t)(512ll << 20) > (int64_t)free_b;
@@ -1296,13 +1422,18 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     {
         const int want = requested_schedule(p);
         if (want == 2 && !fused_possible(p))
-            return fail(CYTVDN_E_INVALID, "the fused schedule covers neither half-isotropic updates nor the mirror "
-                                          "boundary (BC_mode 3); use schedule 0 or 1");
-        if (want != 1 && fused_possible(p) && nIt > 0) {
-            size_t free_b = 0, tot_b = 0;
-            CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+            return fail(CYTVDN_E_INVALID, "the fused schedule does not cover the mirror boundary (BC_mode 3); use "
+                                          "schedule 0 or 1");
+        // The pair (0,1) costs the fused kernel three joint shrinks per voxel instead of one (the forward
+        // neighbours on both far axes are recomputed): measured on config 4, 20.6 ms fused against 16.5 ms in two
+        // passes; (2,3) alone is a wash (16.1 / 16.3 ms).  Auto therefore runs isotropic_R in two passes.
+        const bool fused_pays = !p->isotropic_R;
+        if (want == 2 && nIt > 0) fused = true;                 // asked for: an allocation failure is reported, not hidden
+        else if (want != 1 && fused_possible(p) && fused_pays && nIt > 0) {
+            size_t free_b = 0;
+            if (int rc = available_bytes(&free_b)) return rc;
             const int64_t need = arrays_needed(p, true, data_dev, recon_dev, reference_data && !ref_dev) * (int64_t)nb;
-            fused = want == 2 || need + (int64_t)(512ll << 20) <= (int64_t)free_b;
+            fused = need + (int64_t)(512ll << 20) <= (int64_t)free_b;
         }
     }
 
@@ -1318,7 +1449,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     int nbox = 1;
     {
         const bool can = fused && p->bc_mode == 2 && !p->use_stopping && !reference_data && nIt > 0 &&
-                         (!data_dev || !recon_dev);
+                         (!data_on_dev || !recon_on_dev);
         int want = nb >= ((size_t)256 << 20) ? 16 : 1;
         const char *env = getenv("CYTVDN_PIPELINE");
         if (env && *env) want = atoi(env);
@@ -1435,9 +1566,30 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
     CUDA_TRY(cudaMemsetAsync(sums_d, 0, nsums * sizeof(double), st));
     std::vector<double> sums_h(nsums, 0.0);
-    double *pinned = nullptr;
-    if (p->use_stopping) CUDA_TRY(cudaMallocHost(&pinned, 4 * sizeof(double)));
-    struct PinFree { double *p; void now() { if (p) cudaFreeHost(p); p = nullptr; } ~PinFree() { now(); } } pinfree{pinned};
+    // early stopping: the per-iteration sums come back through a small page-locked buffer (two slots) that the
+    // thread keeps for its lifetime (cudaMallocHost costs ~1 ms), one event per slot
+    static thread_local double *pinned = nullptr;
+    cudaEvent_t stop_ev[2] = {nullptr, nullptr};
+    struct StopEvFree {
+        cudaEvent_t *e;
+        void now() { for (int k = 0; k < 2; ++k) if (e[k]) { cudaEventDestroy(e[k]); e[k] = nullptr; } }
+        ~StopEvFree() { now(); }
+    } stopfree{stop_ev};
+    if (p->use_stopping) {
+        if (!pinned) CUDA_TRY(cudaMallocHost(&pinned, 8 * sizeof(double)));
+        for (auto &e : stop_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    auto below = [&](const double *s4) {                       // cyTVDN.py:189-194 / :236-242
+        const double dl = s4[1] / s4[2];
+        const double dl_t = p->dtype == CYTVDN_F32 ? (double)(float)dl : dl;       // stored in the array dtype
+        return dl_t < p->stopping_relative_change;
+    };
+    // Fused schedule: iteration i+1 never touches what iteration i produced (ping-pong), so from iteration
+    // kSpeculateFrom on it is launched BEFORE the host has seen delta[i]; if delta[i] turns out to be below the
+    // threshold the speculative iteration is discarded -- same result as "stop right after iteration i"
+    // (cyTVDN.py:189-194) without draining the stream once per iteration.  Early iterations, where a stop is
+    // likely and a discarded sweep costs more than a bubble, and the in-place two-pass schedule test synchronously.
+    constexpr int kSpeculateFrom = 8;
 
     auto sse = [&](const void *a, const void *b, double *out) -> int {
         return p->dtype == CYTVDN_F32 ? run_sse<float>(nvox, a, b, out, st, n3, n3p)
@@ -1468,6 +1620,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
             }
             double *s = sums_d + (size_t)i * 4;
             void *u_out = rbuf[rnext];
+            const void *u_before = u_cur;
             if (fused) {
                 if (int rc = cytvdn_fused_iteration(nd, p->shape, p->dtype, orig_d, u_cur, u_out, b[cur], b[1 - cur],
                                                     phase == 0 ? d[cur] : nullptr, phase == 0 ? d[1 - cur] : nullptr,
@@ -1489,12 +1642,24 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
                 if (int rc = sse(ref_d, u_cur, s + 3)) return rc;
             ran[i] = 1;
             ++done[phase];
-            if (p->use_stopping) {                              // cyTVDN.py:189-194 / :236-242
-                CUDA_TRY(cudaMemcpyAsync(pinned, s, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaStreamSynchronize(st));
-                const double dl = pinned[1] / pinned[2];
-                const double dl_t = p->dtype == CYTVDN_F32 ? (double)(float)dl : dl;   // stored in the array dtype
-                if (dl_t < p->stopping_relative_change) break;
+            if (p->use_stopping) {
+                const int slot = it & 1;
+                CUDA_TRY(cudaMemcpyAsync(pinned + 4 * slot, s, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaEventRecord(stop_ev[slot], st));
+                if (fused && it > kSpeculateFrom) {             // this launch was speculative: now look at iteration i-1
+                    CUDA_TRY(cudaEventSynchronize(stop_ev[slot ^ 1]));
+                    if (below(pinned + 4 * (slot ^ 1))) {       // it met the criterion: iteration i never happened
+                        ran[i] = 0;
+                        --done[phase];
+                        cur = 1 - cur;
+                        rnext = 1 - rnext;
+                        u_cur = u_before;
+                        break;
+                    }
+                } else if (!(fused && it == kSpeculateFrom)) {  // (at kSpeculateFrom the test moves one iteration back)
+                    CUDA_TRY(cudaEventSynchronize(stop_ev[slot]));
+                    if (below(pinned + 4 * slot)) break;
+                }
             }
         }
     }
@@ -1575,7 +1740,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     }
     side.now();
     evfree.now();
-    pinfree.now();
+    stopfree.now();
     restore.now();
     mark("results delivered");
     // cudaFree of the ~80 GB arena: 25-40 ms, now and then several hundred (tools/e2e_trace.py).  Handing it to a
@@ -1584,6 +1749,12 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     pool0.release();
     mark("arenas freed");
     return CYTVDN_OK;
+}
+
+int cytvdn_denoise_sharded_streamed(const cytvdn_denoise_params *, int, const int *, const void *, void *, double *,
+                                    double *, int32_t *, double *)
+{
+    return fail(CYTVDN_E_UNSUPPORTED, "sharded out-of-core schedule: not built yet");
 }
 
 // ---- host-side plans (no GPU needed) ------------------------------------------------------------
@@ -1613,6 +1784,67 @@ int cytvdn_stream_plan(const cytvdn_denoise_params *p, int64_t budget_bytes, int
 }
 
 // ---- small CUDA helpers -----------------------------------------------------------------------
+int cytvdn_workspace_reserve(int64_t bytes)
+{
+    if (bytes < 0) return fail(CYTVDN_E_INVALID, "bytes < 0");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_res_mutex);
+    Reserved &r = g_reserved[dev];
+    if (r.refs > 0) return fail(CYTVDN_E_INVALID, "the reserved workspace is in use by a running call");
+    if (r.base && r.size >= (size_t)bytes) return CYTVDN_OK;          // big enough already
+    if (r.base) { cudaFree(r.base); r = Reserved(); }
+    if (bytes == 0) return CYTVDN_OK;
+    cudaError_t e = cudaMalloc((void **)&r.base, (size_t)bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        r = Reserved();
+        return fail(CYTVDN_E_NOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+    }
+    r.size = (size_t)bytes;
+    return CYTVDN_OK;
+}
+
+int cytvdn_workspace_release(void)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceSynchronize());
+    {
+        std::lock_guard<std::mutex> lk(g_res_mutex);
+        auto it = g_reserved.find(dev);
+        if (it != g_reserved.end()) {
+            if (it->second.refs > 0) return fail(CYTVDN_E_INVALID, "the reserved workspace is in use by a running call");
+            if (it->second.base) cudaFree(it->second.base);
+            g_reserved.erase(it);
+        }
+    }
+    drop_workspaces(dev);
+    return CYTVDN_OK;
+}
+
+int cytvdn_workspace_info(int64_t *reserved_bytes, int64_t *in_use_bytes)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_res_mutex);
+    auto it = g_reserved.find(dev);
+    if (reserved_bytes) *reserved_bytes = it == g_reserved.end() ? 0 : (int64_t)it->second.size;
+    if (in_use_bytes) *in_use_bytes = it == g_reserved.end() ? 0 : (int64_t)it->second.used;
+    return CYTVDN_OK;
+}
+
+int cytvdn_last_trace(double *ms, const char **what, int capacity, int *count)
+{
+    if (!count) return fail(CYTVDN_E_INVALID, "count is NULL");
+    *count = g_trace_n;
+    for (int k = 0; k < g_trace_n && k < capacity; ++k) {
+        if (ms) ms[k] = g_trace_ms[k];
+        if (what) what[k] = g_trace_what[k];
+    }
+    return CYTVDN_OK;
+}
+
 int cytvdn_malloc(void **ptr, int64_t bytes)
 {
     if (!ptr || bytes < 0) return fail(CYTVDN_E_INVALID, "bad argument");
@@ -1677,3 +1909,20 @@ int cytvdn_mem_info(int64_t *free_bytes, int64_t *total_bytes)
 }
 
 }  // extern "C"
+
+// ---- helpers for the other translation units (internal.hh) -----------------------------------------
+namespace cytvdn_internal {
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int pinned_alloc(void **out, size_t bytes) { return ::pinned_alloc(out, bytes); }
+int pinned_free(void *p) { return ::pinned_free(p); }
+}  // namespace cytvdn_internal

@@ -218,7 +218,237 @@ const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
                 so += absval(us.v[v]);
             }
         }
-        if (c.active) st_stream<T, VW>(P.uout + e, un);
+        if (S.own_store ? c.owned : c.active) st_stream<T, VW>(P.uout + e, un);
+        if (c.owned) {
+            acc[0] += (double)sb;
+            acc[1] += (double)sd;
+            acc[2] += (double)so;
+        }
+    }
+    reduce_finish<3>(acc, P.W);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused iteration with half-isotropic axis pairs (halfisotropic.pyx:63-95, :146-186 fused with utils.pyx:90-104).
+//
+// The pair update couples two axes: (dp, dq) = ((u - u[x-e_p]) + b_p, (u - u[x-e_q]) + b_q) is shrunk jointly.  The
+// divergence needs b'_p at x + e_p, and that value depends on BOTH differences at x + e_p, so next to what the
+// anisotropic fused kernel loads (u, b_p, d_p at x + e_p) a pair needs the partner's data there: b_q[x + e_p] and
+// the diagonal neighbour u[x + e_p - e_q] -- two more L2 hits per far axis of a pair; for the fast axis the partner
+// data are the thread's own vectors and shuffles.  Pair shrinks per voxel: 3 for the pair (0,1), 2 for (2,3)
+// (b'_3[x + e_3] is the own value of the next voxel), against 2 in the two-pass kernel -- affordable only with the
+// float-float hypot and the shared-reciprocal divisions of kernels.cuh (the FP64 version made this kernel slower
+// than two passes).  Jia-Zhao boundary on the pair's axes (the reference's iso kernels know no other); an axis that
+// is not in a pair is updated exactly as in tv_fused_kernel.  4-D arrays, full vector width only.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef FUSED_ISO_MINB
+#define FUSED_ISO_MINB 2
+#endif
+template <typename T, bool FISTA, bool ISO_R, bool ISO_Q>
+__global__ void __launch_bounds__(kBlock, FUSED_ISO_MINB)
+tv_fused_iso_kernel(const FusedParams<T> P)
+{
+    constexpr int VW = 16 / (int)sizeof(T);
+    const Sweep &S = P.S;
+    const int lane = threadIdx.x & 31;
+    double acc[3] = {0.0, 0.0, 0.0};
+    const T rclipR = clip_rcp(P.clip[0]), rclipQ = clip_rcp(P.clip[2]);
+    auto fista = [&](T v, T d) -> T { return FISTA ? (v + P.tk * (v - d)) : v; };
+
+    TileSched sched{P.W.ticket + 1, S.dynamic, 0};
+    for (int32_t t = sched.first(); t < S.ntiles; t = sched.template advance<true>(t)) {
+        sched.prefetch();
+        const Coord c = locate<VW>(S, t);
+        const int64_t e = c.e;
+        const int32_t coord[3] = {c.i, c.j, c.k};
+        const int32_t extent[3] = {S.n0, S.n1, S.n2};
+        const int64_t stride[3] = {S.st0, S.st1, (int64_t)S.n3p};
+        int64_t poff[3], yoff[3];
+        bool at_end[3], at0[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int64_t span = (int64_t)(extent[d] - 1) * stride[d];
+            at0[d] = coord[d] == 0;
+            poff[d] = !at0[d] ? e - stride[d] : (P.bc[d] == 2 ? e : e + span);
+            at_end[d] = coord[d] == extent[d] - 1;
+            yoff[d] = at_end[d] ? e - span : e + stride[d];
+        }
+
+        // ---------------- phase 1: own voxels ------------------------------------------------------------
+        const Vec<T, VW> us = ld_ro<T, VW>(P.uin + e);
+        const Vec<T, VW> f = ld_ro<T, VW>(P.f + e);
+        const Vec<T, VW> b3 = ld_ro<T, VW>(P.bin[3] + e);
+        Vec<T, VW> d3;
+        if (FISTA) d3 = ld_ro<T, VW>(P.din[3] + e);
+        Vec<T, VW> bs[3], ds[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            bs[d] = ld_ro<T, VW>(P.bin[d] + e);
+            if (FISTA) ds[d] = ld_ro<T, VW>(P.din[d] + e);
+        }
+        T left = __shfl_up_sync(0xffffffffu, us.v[VW - 1], 1);
+        // ---------------- phase 2: neighbours, one memory latency later (see tv_fused_kernel) -------------
+        if (__syncthreads_or(left != left) == 0x5a5a5a5a) return;       // never taken
+        Vec<T, VW> pv[3], uy[3], by[3], dy[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            pv[d] = ld_ro_ordered<T, VW>(P.uin + poff[d]);
+            uy[d] = ld_ro_ordered<T, VW>(P.uin + yoff[d]);
+            by[d] = ld_ro_ordered<T, VW>(P.bin[d] + yoff[d]);
+            if (FISTA) dy[d] = ld_ro_ordered<T, VW>(P.din[d] + yoff[d]);
+        }
+        // partner data of the pairs at the forward neighbours
+        Vec<T, VW> ux0, bq0, ux1, bq1, b3y;      // pair (0,1): u[x+e0-e1], b_1[x+e0]; u[x+e1-e0], b_0[x+e1]; pair (2,3): b_3[x+e2]
+        if (ISO_R) {
+            ux0 = ld_ro_ordered<T, VW>(P.uin + (at0[1] ? yoff[0] : yoff[0] - S.st1));      // Jia-Zhao: difference 0 at index 0
+            bq0 = ld_ro_ordered<T, VW>(P.bin[1] + yoff[0]);
+            ux1 = ld_ro_ordered<T, VW>(P.uin + (at0[0] ? yoff[1] : yoff[1] - S.st0));
+            bq1 = ld_ro_ordered<T, VW>(P.bin[0] + yoff[1]);
+        }
+        if (ISO_Q) b3y = ld_ro_ordered<T, VW>(P.bin[3] + yoff[2]);
+
+        // ---------------- differences + accumulators: own voxels ---------------------------------------------
+        if (c.l0 == 0) left = (P.bc[3] == 2) ? us.v[0] : __ldg(P.uin + e + (S.n3 - 1));
+        else if (lane == 0) left = __ldg(P.uin + e - 1);
+        Vec<T, VW> vs[4];                                   // (u - u[x - e_d]) + b_d, then shrunk / clipped (= new d)
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            vs[3].v[v] = (us.v[v] - (v == 0 ? left : us.v[v - 1])) + b3.v[v];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) vs[d].v[v] = (us.v[v] - pv[d].v[v]) + bs[d].v[v];
+        }
+        // ---------------- the same at the forward neighbours x + e_d of the far axes ---------------------------
+        Vec<T, VW> fa[3], fp[3];                            // difference on axis d at x + e_d / its partner's there
+        bool zero[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            zero[d] = at_end[d] && ((P.zero_wrap >> d) & 1);
+            const bool jz0 = at_end[d] && P.bc[d] == 2;     // neighbour sits at index 0: its own difference is 0
+            T left_y = T(0);                                // pair (2,3): element before uy[2].v[0] on the next row
+            if (d == 2 && ISO_Q) {
+                left_y = __shfl_up_sync(0xffffffffu, uy[2].v[VW - 1], 1);
+                if (c.l0 == 0) left_y = uy[2].v[0];                             // Jia-Zhao on axis 3
+                else if (lane == 0) left_y = __ldg(P.uin + yoff[2] - 1);
+            }
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                fa[d].v[v] = (uy[d].v[v] - (jz0 ? uy[d].v[v] : us.v[v])) + by[d].v[v];
+                if (d == 0 && ISO_R) fp[0].v[v] = (uy[0].v[v] - ux0.v[v]) + bq0.v[v];       // axis 1 at x + e0
+                if (d == 1 && ISO_R) fp[1].v[v] = (uy[1].v[v] - ux1.v[v]) + bq1.v[v];       // axis 0 at x + e1
+                if (d == 2 && ISO_Q) fp[2].v[v] = (uy[2].v[v] - (v == 0 ? left_y : uy[2].v[v > 0 ? v - 1 : 0])) + b3y.v[v];
+            }
+        }
+        // ---------------- one more site on the fast axis: the voxel after this vector, where no lane owns it ----
+        // (row end: the row's voxel 0, wrap; lane 31: first voxel of the next warp's vector)
+        const bool edge_wrap = c.row_end && !(P.zero_wrap & 8), edge_next = !c.row_end && lane == 31;
+        T e3 = T(0), e2 = T(0), ed3 = T(0);                 // differences on axes 3 / 2 there, and d_3 there
+        if (edge_wrap || edge_next) {
+            const int64_t y = edge_wrap ? e - c.l0 : e + VW;
+            const T uyy = __ldg(P.uin + y);
+            T ulast = us.v[0];
+#pragma unroll
+            for (int v = 1; v < VW; ++v)
+                if (v == c.vl) ulast = us.v[v];
+            const T prev3 = edge_wrap ? ((P.bc[3] == 2) ? uyy : ulast) : us.v[VW - 1];
+            e3 = (uyy - prev3) + __ldg(P.bin[3] + y);
+            if (ISO_Q) e2 = (uyy - (at0[2] ? uyy : __ldg(P.uin + y - S.n3p))) + __ldg(P.bin[2] + y);
+            if (FISTA) ed3 = __ldg(P.din[3] + y);
+        }
+        // ---------------- clip or joint shrink, everything this thread holds ------------------------------------
+        T amax = T(0);
+        if (ISO_R || ISO_Q) {
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                if (ISO_R) {
+                    pair_track(amax, vs[0].v[v], vs[1].v[v]);
+                    pair_track(amax, fa[0].v[v], fp[0].v[v]);
+                    pair_track(amax, fa[1].v[v], fp[1].v[v]);
+                }
+                if (ISO_Q) {
+                    pair_track(amax, vs[2].v[v], vs[3].v[v]);
+                    pair_track(amax, fa[2].v[v], fp[2].v[v]);
+                }
+            }
+            if (ISO_Q) pair_track(amax, e2, e3);
+        }
+        const bool fastR = ISO_R && pair_fast_ok(amax, rclipR), fastQ = ISO_Q && pair_fast_ok(amax, rclipQ);
+        if (ISO_R) {
+            shrink_vec<T, VW>(vs[0], vs[1], P.clip[0], rclipR, fastR);
+            shrink_vec<T, VW>(fa[0], fp[0], P.clip[0], rclipR, fastR);
+            shrink_vec<T, VW>(fp[1], fa[1], P.clip[0], rclipR, fastR);          // (axis 0, axis 1) order
+        } else {
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                vs[0].v[v] = clipval(vs[0].v[v], P.clip[0]); vs[1].v[v] = clipval(vs[1].v[v], P.clip[1]);
+                fa[0].v[v] = clipval(fa[0].v[v], P.clip[0]); fa[1].v[v] = clipval(fa[1].v[v], P.clip[1]);
+            }
+        }
+        if (ISO_Q) {
+            shrink_vec<T, VW>(vs[2], vs[3], P.clip[2], rclipQ, fastQ);
+            shrink_vec<T, VW>(fa[2], fp[2], P.clip[2], rclipQ, fastQ);
+            if (edge_wrap || edge_next) {
+                if (fastQ) shrink_fast(e2, e3, P.clip[2], rclipQ);
+                else shrink_exact(e2, e3, P.clip[2]);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                vs[2].v[v] = clipval(vs[2].v[v], P.clip[2]); vs[3].v[v] = clipval(vs[3].v[v], P.clip[3]);
+                fa[2].v[v] = clipval(fa[2].v[v], P.clip[2]);
+            }
+            e3 = clipval(e3, P.clip[3]);
+        }
+        // ---------------- FISTA extrapolation, stores, divergence terms ------------------------------------------
+        Vec<T, VW> ns[4];
+        T sb = T(0);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const Vec<T, VW> &dd = d == 3 ? d3 : ds[d < 3 ? d : 0];
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                ns[d].v[v] = fista(vs[d].v[v], FISTA ? dd.v[v] : T(0));
+                if (v <= c.vl) sb += absval(ns[d].v[v]);
+            }
+            if (c.active) {
+                st_stream<T, VW>(P.bout[d] + e, ns[d]);
+                if (FISTA) st_stream<T, VW>(P.dout[d] + e, vs[d]);
+            }
+        }
+        Vec<T, VW> term[4];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                T nf = fista(fa[d].v[v], FISTA ? dy[d].v[v] : T(0));
+                if (zero[d]) nf = T(0);
+                term[d].v[v] = P.w[d] * (ns[d].v[v] - nf);
+            }
+        T right3 = __shfl_down_sync(0xffffffffu, ns[3].v[0], 1);
+        const T edge = fista(e3, ed3);                      // b'_3 at the edge site
+        if (edge_next) right3 = edge;
+        const T wrap3 = edge_wrap ? edge : T(0);
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            T fwd = v == VW - 1 ? right3 : ns[3].v[v + 1 < VW ? v + 1 : v];
+            if (c.row_end && v == c.vl) fwd = wrap3;
+            term[3].v[v] = P.w[3] * (ns[3].v[v] - fwd);
+        }
+
+        // ---------------- reconstruction update ------------------------------------------------------------
+        Vec<T, VW> un;
+        T sd = T(0), so = T(0);
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            T s = term[0].v[v] + term[1].v[v];
+            s = s + term[2].v[v];
+            s = s + term[3].v[v];
+            un.v[v] = f.v[v] - s;
+            if (v <= c.vl) {
+                sd += absval(un.v[v] - us.v[v]);
+                so += absval(us.v[v]);
+            }
+        }
+        if (S.own_store ? c.owned : c.active) st_stream<T, VW>(P.uout + e, un);
         if (c.owned) {
             acc[0] += (double)sb;
             acc[1] += (double)sd;

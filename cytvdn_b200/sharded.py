@@ -361,8 +361,10 @@ class CudaShard:
         self.fused = fused
         if fused:       # second state set: the fused iteration is out of place (ping-pong)
             self.recon2 = carve(False)
-            self.b2 = [carve(False) for _ in range(4)]
-            self.d2 = [carve(False) for _ in range(4)] if fista else None
+            # zeroed: the lower overlap plane of these is never swept (fused_boxes skips plane 0) and must not hold
+            # uninitialised memory that return_state / checksums would expose
+            self.b2 = [carve(True) for _ in range(4)]
+            self.d2 = [carve(True) for _ in range(4)] if fista else None
             self.bp2 = (C.c_void_p * 4)(*[t.data_ptr() for t in self.b2])
             self.dp2 = (C.c_void_p * 4)(*[t.data_ptr() for t in self.d2]) if fista else None
             self.first = True       # iteration 0 reads recon == orig
@@ -539,9 +541,281 @@ def _run_iteration_simple(sh: CudaShard, it, tkr, fista, group):
             unpack()
 
 
+# ------------------------------------------------------------------------------------------------
+# The C-ABI shard engine (csrc/cytvdn_shard.cu): the sharded loop lives in the library, the exchange is done by the
+# copy engines through peer pointers under the interior sweep.  Python only moves the 128-byte handles between the
+# ranks (torch.distributed as plumbing) and adds up three doubles per iteration at the end.
+# ------------------------------------------------------------------------------------------------
+class EngineShard:
+    """One rank's ``cytvdn_shard`` (1-D split of scan axis 0, fused schedule)."""
+
+    def __init__(self, gshape, world, rank, mu, lam=None, dtype=np.float32, fista=True, max_iters=1, periodic=False,
+                 device=None):
+        from . import _lib
+        self._lib, self.lib = _lib, _lib.load()
+        _lib.require_gpu()
+        dt = np.dtype(dtype)
+        mu = np.asarray(mu, dtype=dt)
+        lam = (mu * 1.0 / 32.0) if lam is None else np.asarray(lam, dtype=dt)      # cyTVDN.py:67-68
+        P = _lib.ShardParams()
+        P.dtype = 0 if dt == np.float32 else 1
+        P.world, P.rank, P.periodic, P.fista = int(world), int(rank), int(bool(periodic)), int(bool(fista))
+        P.max_iters = max(1, int(max_iters))
+        P.device = -1 if device is None else int(device)
+        for k in range(4):
+            P.gshape[k] = int(gshape[k])
+            P.clip[k] = float((1.0 / lam)[k])
+            P.lambda_mu[k] = float((lam / mu).astype(dt)[k])
+        if device is None:
+            d = C.c_int(0)
+            _lib.check(self.lib.cytvdn_get_device(C.byref(d)))
+            device = d.value
+        self._dev = int(device)
+        self.h = C.c_void_p()
+        _lib.check(self.lib.cytvdn_shard_create(C.byref(P), C.byref(self.h)))
+        self.dtype, self.world, self.rank, self.gshape = dt, int(world), int(rank), tuple(int(v) for v in gshape)
+        self.refresh()
+
+    def refresh(self):
+        o = (C.c_int64 * 12)()
+        self._lib.check(self.lib.cytvdn_shard_info(self.h, o))
+        (self.n_local, self.own_lo, self.own_hi, self.valid_lo, self.valid_hi, self.read_lo, self.has_lo, self.has_hi,
+         self.arena_bytes, self.n3p, self.launches, self.it_run) = [int(v) for v in o]
+        return self
+
+    @property
+    def local_shape(self):
+        return (self.n_local,) + self.gshape[1:]
+
+    @property
+    def owned_shape(self):
+        return (self.own_hi - self.own_lo,) + self.gshape[1:]
+
+    def export(self) -> bytes:
+        h = (C.c_ubyte * 128)()
+        self._lib.check(self.lib.cytvdn_shard_export(self.h, h))
+        return bytes(h)
+
+    def connect(self, side: int, handle: bytes):
+        self._lib.check(self.lib.cytvdn_shard_connect(self.h, int(side), (C.c_ubyte * 128)(*handle)))
+
+    def connect_all(self, handles):
+        """``handles[r]`` = rank r's export; connects the lower and the upper neighbour (wrapping when periodic)."""
+        self.connect(0, handles[(self.rank - 1) % self.world])
+        self.connect(1, handles[(self.rank + 1) % self.world])
+
+    def array_ptr(self, which, set_=0, axis=0) -> int:
+        p = C.c_void_p()
+        self._lib.check(self.lib.cytvdn_shard_array(self.h, {"orig": 0, "recon": 1, "b": 2, "d": 3}[which], set_, axis, C.byref(p)))
+        return p.value
+
+    def array(self, which, set_=0, axis=0):
+        """torch view of an internal device array (rows padded to ``n3p``)."""
+        import torch
+        shape = (self.n_local,) + self.gshape[1:3] + (self.n3p,)
+        typestr = "<f4" if self.dtype == np.float32 else "<f8"
+        dev = torch.device("cuda", self.device_index())
+        return torch.as_tensor(_DevArray(self.array_ptr(which, set_, axis), shape, typestr), device=dev)
+
+    def device_index(self):
+        return self._dev
+
+    def load(self, block=None):
+        """``block``: stored planes (owned + overlap) with dense rows -- CUDA tensor, NumPy array (pinned for speed) or
+        None when ``orig`` was written in place."""
+        if block is None:
+            ptr = None
+        elif hasattr(block, "data_ptr"):
+            import torch
+            assert block.is_contiguous() and tuple(block.shape) == self.local_shape, (tuple(block.shape), self.local_shape)
+            torch.cuda.current_stream(block.device).synchronize()     # the shard copies on its own stream
+            ptr = block.data_ptr()
+        else:
+            assert block.flags["C_CONTIGUOUS"] and block.dtype == self.dtype and tuple(block.shape) == self.local_shape
+            ptr = block.ctypes.data
+        self._keep = block
+        self._lib.check(self.lib.cytvdn_shard_load(self.h, C.c_void_p(ptr) if ptr else None))
+
+    def load_synth(self, seed=2, counts=500.0):
+        """Generate this shard's planes of the synthetic 4D-STEM array straight into ``orig`` (dense rows only)."""
+        import torch
+        from . import synth
+        assert self.n3p == self.gshape[3] and not (self.read_lo < 0 or self.read_lo + self.n_local > self.gshape[0])
+        mod, templ = synth._stem_tables(self.gshape)
+        tmod, ttem = torch.from_numpy(mod).cuda(), torch.from_numpy(templ).cuda()
+        gs = (C.c_int64 * 4)(*self.gshape)
+        st = torch.cuda.current_stream().cuda_stream
+        self._lib.check(self.lib.cytvdn_synth_counts(gs, self.read_lo, self.n_local, 0 if self.dtype == np.float32 else 1,
+                                                     tmod.data_ptr(), ttem.data_ptr(), float(counts), int(seed),
+                                                     C.c_void_p(self.array_ptr("orig")), st))
+        torch.cuda.current_stream().synchronize()
+        self.load(None)
+
+    def iterate(self, n_fista=0, n_plain=0):
+        self._lib.check(self.lib.cytvdn_shard_iterate(self.h, int(n_fista), int(n_plain)))
+
+    def synchronize(self):
+        self._lib.check(self.lib.cytvdn_shard_synchronize(self.h))
+
+    def sums(self, n) -> np.ndarray:
+        out = np.zeros((max(n, 1), 3), dtype=np.float64)
+        self._lib.check(self.lib.cytvdn_shard_sums(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), int(n)))
+        return out[:n]
+
+    def store(self, out):
+        """Owned planes of the current reconstruction into ``out`` (CUDA tensor or NumPy array of ``owned_shape``)."""
+        if hasattr(out, "data_ptr"):
+            assert out.is_contiguous() and tuple(out.shape) == self.owned_shape
+            ptr = out.data_ptr()
+        else:
+            assert out.flags["C_CONTIGUOUS"] and out.dtype == self.dtype and tuple(out.shape) == self.owned_shape
+            ptr = out.ctypes.data
+        self._lib.check(self.lib.cytvdn_shard_store(self.h, C.c_void_p(ptr)))
+        return out
+
+    def profile(self, on=True):
+        self._lib.check(self.lib.cytvdn_shard_profile(self.h, int(on)))
+
+    def timeline(self, n) -> np.ndarray:
+        out = np.zeros((max(n, 1), 6), dtype=np.float64)
+        self._lib.check(self.lib.cytvdn_shard_timeline(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), int(n)))
+        return out[:n]
+
+    def close(self):
+        if self.h:
+            self.lib.cytvdn_shard_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def _split_iterations(iterations, FISTA):
+    if type(iterations) in (list, tuple):
+        return int(iterations[0]), int(iterations[1])
+    return int(iterations * bool(FISTA)), int(iterations * (not FISTA))
+
+
+def denoise4D_engine(block, mu, iterations=10, FISTA=True, stopping_relative_change=None, *, gshape, group=None, lam=None,
+                     periodic=False, out=None, engine=None, return_engine=False):
+    """Sharded ``denoise4D`` through the C-ABI shard engine -- call it on every rank (one process per GPU).
+
+    ``block``: this rank's stored planes (owned + one overlap plane per neighbour, ``ShardPlan.read_global``) as a
+    contiguous CUDA tensor or a (pinned) NumPy array.  Returns ``(recon_owned, b_norm, delta_recon)``: the rank's OWNED
+    planes (``out`` or a new array of the input's kind) and the global scalars.  The halo exchange is done inside the
+    library by the copy engines over NVLink (CUDA IPC peer pointers); torch.distributed only carries the handles and
+    one all-reduce of 3 doubles per iteration (per iteration only with ``stopping_relative_change``)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    nF, nU = _split_iterations(iterations, FISTA)
+    n = nF + nU
+    is_t = hasattr(block, "data_ptr")
+    dt = np.dtype(str(block.dtype).replace("torch.", "")) if is_t else block.dtype
+    dev = block.device if is_t else torch.device("cuda", torch.cuda.current_device())
+    # the three sums per iteration travel over whatever backend the group has (gloo reduces host tensors)
+    red_dev = dev if (world > 1 and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    own_engine = engine is None
+    if own_engine:
+        engine = EngineShard(gshape, world, rank, mu, lam, dt, fista=nF > 0, max_iters=max(n, 1), periodic=periodic,
+                             device=dev.index)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, engine.export(), group=group)
+        else:
+            handles = [engine.export()]
+        engine.connect_all(handles)
+    try:
+        engine.load(block)
+        if world > 1:
+            dist.barrier(group=group)          # every rank's flags and state are in place before anyone pushes
+        ran = np.zeros(n, dtype=bool)
+        glob = np.zeros((max(n, 1), 3))
+        if stopping_relative_change is None:
+            engine.iterate(nF, nU)
+            ran[:] = True
+        else:
+            stop = False
+            for phase, count in ((0, nF), (1, nU)):
+                for j in range(count):
+                    it = j if phase == 0 else nF + j
+                    engine.iterate(1 if phase == 0 else 0, 0 if phase == 0 else 1)
+                    ran[it] = True
+                    k = engine.refresh().it_run                # sums are stored per iteration that RAN
+                    s = torch.from_numpy(engine.sums(k)[k - 1].copy()).to(red_dev)
+                    if world > 1:
+                        dist.all_reduce(s, group=group)
+                    s = s.cpu().numpy()
+                    dl = float(s[1] / s[2])
+                    if dt == np.float32:
+                        dl = float(np.float32(dl))
+                    if dl < stopping_relative_change:      # cyTVDN.py:189-194: leaves THIS phase only
+                        break
+        done = int(ran.sum())
+        loc = np.zeros((max(n, 1), 3))
+        # sums of the iterations that ran are stored consecutively (it_run counts them)
+        got = engine.sums(engine.refresh().it_run)
+        loc[np.nonzero(ran)[0]] = got[:done]
+        g = torch.from_numpy(loc).to(red_dev)
+        if world > 1:
+            dist.all_reduce(g, group=group)
+        g = g.cpu().numpy()
+        with np.errstate(all="ignore"):
+            b_norm = np.where(ran, g[:n, 0], 0.0).astype(dt)
+            delta = np.where(ran, g[:n, 1] / g[:n, 2], 0.0).astype(dt)
+        if out is None:
+            out = (torch.empty(engine.owned_shape, dtype=block.dtype, device=dev) if is_t
+                   else np.empty(engine.owned_shape, dtype=dt))
+        engine.store(out)
+        if world > 1:
+            dist.barrier(group=group)          # nobody frees (or re-loads) an arena a neighbour still pushes into
+        if return_engine:
+            return out, b_norm, delta, engine
+        return out, b_norm, delta
+    finally:
+        if own_engine and not return_engine:
+            engine.close()
+
+
+def emulate_engine_on_one_device(gdata, mu, world, iterations=10, FISTA=True, periodic=False, lam=None):
+    """All ranks of the shard engine in THIS process on one device (handles resolve to plain pointers): validates the
+    engine -- box order, flags, pushes, owned-only stores -- where fewer GPUs than ranks exist.  Needs
+    CUDA_DEVICE_MAX_CONNECTIONS >= 2*world so that the streams do not share hardware queues (a spinning wait kernel
+    must never sit in front of the work it waits for).  Returns (assembled recon, b_norm, delta)."""
+    import torch
+    nF, nU = _split_iterations(iterations, FISTA)
+    n = nF + nU
+    dt = np.float32 if gdata.dtype == torch.float32 else np.float64
+    eng = [EngineShard(gdata.shape, world, r, mu, lam, dt, fista=nF > 0, max_iters=max(n, 1), periodic=periodic)
+           for r in range(world)]
+    try:
+        handles = [e.export() for e in eng]
+        n0 = gdata.shape[0]
+        for e in eng:
+            e.connect_all(handles)
+            idx = [(e.read_lo + i) % n0 for i in range(e.n_local)]
+            e.load(gdata.index_select(0, torch.as_tensor(idx, device=gdata.device)).contiguous())
+        for phase, cnt in ((0, nF), (1, nU)):
+            for _ in range(cnt):
+                for e in eng:                    # iteration by iteration across the ranks, like cytvdn_denoise_sharded
+                    e.iterate(1 if phase == 0 else 0, 0 if phase == 0 else 1)
+        out = torch.empty_like(gdata)
+        tot = np.zeros((max(n, 1), 3))
+        for e in eng:
+            e.store(out[e.valid_lo:e.valid_hi])
+            tot[:n] += e.sums(n)
+        with np.errstate(all="ignore"):
+            return out, tot[:n, 0].copy(), (tot[:n, 1] / tot[:n, 2]).copy()
+    finally:
+        for e in eng:
+            e.synchronize() if e.h else None
+        for e in eng:
+            e.close()
+
+
 def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_change=None, *, plan: ShardPlan,
-                      group=None, lam=None, overlap=True, return_state=False, schedule="fused"):
-    """Sharded counterpart of ``denoise4D`` -- call it on every rank of the process group.
+                      group=None, lam=None, overlap=True, return_state=False, schedule="fused", engine=False):
+    """Sharded counterpart of ``denoise4D`` over torch.distributed / NCCL -- call it on every rank of the process group.
+    (Round 1's schedule, kept for 2-D ``(wx, wy)`` grids, the reference-structured two-pass iteration and as the
+    cross-check of the C-ABI engine; ``denoise4D_engine`` is the default path for 1-D splits.  ``engine`` must be False.)
 
     ``shard``: this rank's block INCLUDING its overlap planes (``plan.read_global`` of the global
     array), a contiguous CUDA tensor.  Returns ``(recon_local, b_norm, delta_recon)`` where
@@ -554,6 +828,7 @@ def denoise4D_sharded(shard, mu, iterations=10, FISTA=True, stopping_relative_ch
     """
     import torch
     import torch.distributed as dist
+    assert not engine, "denoise4D_sharded is the NCCL path; use denoise4D_engine for the C-ABI engine"
     unaccelerated = not FISTA
     if type(iterations) in (list, tuple):
         FISTA, unaccelerated = True, True

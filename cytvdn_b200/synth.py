@@ -21,6 +21,29 @@ from . import _lib
 _IH_SCALE = np.float32(2.6429137e-05)      # 1 / sqrt(4 * (65536^2 - 1) / 12): Irwin-Hall(4) of 16-bit fields
 
 
+def eels_clean(shape=(128, 128, 1024), dose=1000.0, dtype=np.float32):
+    """Noise-free expectation of ``eels_cube`` (float32 by default; e.g. to draw the Poisson noise on the device)."""
+    X, Y, E = shape
+    e = np.arange(E, dtype=np.float64)
+    bg = (e + 0.05 * E) ** -1.5
+    bg /= bg.max()
+    edges = []
+    for ek in (0.35 * E, 0.65 * E):
+        ed = np.zeros(E)
+        m = e > ek
+        ed[m] = (e[m] - ek + 1.0) ** -0.6
+        edges.append(ed)
+    x = np.arange(X, dtype=np.float64)[:, None]
+    y = np.arange(Y, dtype=np.float64)[None, :]
+    w1 = (0.5 * (1 + np.tanh((x - X / 2) / max(X / 16, 1e-9))) * np.ones((1, Y))).astype(dtype)
+    w2 = (0.5 * (1 + np.sin(2 * np.pi * y / max(Y / 2, 1e-9))) * np.ones((X, 1))).astype(dtype)
+    out = np.empty(shape, dtype=dtype)
+    bg_d, e1, e2 = (dose * bg).astype(dtype), (dose * 0.25 * edges[0]).astype(dtype), (dose * 0.15 * edges[1]).astype(dtype)
+    for i in range(X):                      # plane by plane: no float64 temporaries of the full cube
+        out[i] = bg_d[None, :] + w1[i][:, None] * e1[None, :] + w2[i][:, None] * e2[None, :]
+    return out
+
+
 def eels_cube(shape=(128, 128, 1024), seed=0, dose=1000.0, gain=1.0, dtype=np.float32):
     X, Y, E = shape
     rng = np.random.default_rng(seed)

@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import F32, F64, DenoiseParams, StepOpts, check
 
 __all__ = [
-    "denoise3D", "denoise4D", "check_memory", "pinned_empty",
+    "denoise3D", "denoise4D", "check_memory", "pinned_empty", "workspace_reserve", "workspace_release",
     "accumulator_update_4D", "accumulator_update_4D_FISTA",
     "accumulator_update_3D", "accumulator_update_3D_FISTA",
     "iso_accumulator_update_4D", "iso_accumulator_update_4D_FISTA",
@@ -122,29 +122,35 @@ class _Staged:
         lib = self.lib
         self._ctx = _on_device(self.device)
         self._ctx.__enter__()
+        # ONE device allocation for everything this call stages (host arrays + the reduction slots)
+        hosts, total = [], 256
         for a in self.arrays:
+            if a is None or (_is_torch(a) and a.is_cuda):
+                hosts.append(None)
+                continue
+            h = a.numpy() if _is_torch(a) else a
+            if not h.flags["C_CONTIGUOUS"]:
+                raise ValueError("ndarray is not C-contiguous")
+            hosts.append((h, total))
+            total += (h.nbytes + 255) // 256 * 256
+        base = C.c_void_p()
+        check(lib.cytvdn_malloc(C.byref(base), total))
+        self.owned.append(base)
+        self.sums = C.c_void_p(base.value)                      # first 256 bytes: up to 8 doubles of sums
+        for a, hv in zip(self.arrays, hosts):
             if a is None:
                 self.ptrs.append(None)
                 self.host_views.append(None)
-            elif _is_torch(a) and a.is_cuda:
+            elif hv is None:
                 if not a.is_contiguous():
                     raise ValueError("ndarray is not C-contiguous")
                 self.ptrs.append(a.data_ptr())
                 self.host_views.append(None)
             else:
-                h = a.numpy() if _is_torch(a) else a
-                if not h.flags["C_CONTIGUOUS"]:
-                    raise ValueError("ndarray is not C-contiguous")
-                p = C.c_void_p()
-                check(lib.cytvdn_malloc(C.byref(p), h.nbytes))
-                self.owned.append(p)
-                check(lib.cytvdn_memcpy(p, h.ctypes.data, h.nbytes, self.stream))
-                self.ptrs.append(p.value)
+                h, off = hv
+                check(lib.cytvdn_memcpy(C.c_void_p(base.value + off), h.ctypes.data, h.nbytes, self.stream))
+                self.ptrs.append(base.value + off)
                 self.host_views.append(h)
-        p = C.c_void_p()
-        check(lib.cytvdn_malloc(C.byref(p), 8 * 8))
-        self.owned.append(p)
-        self.sums = p
         return self
 
     def read_sums(self, n):
@@ -296,6 +302,49 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------
+# optional reservation of the device working set (repeated calls skip cudaMalloc / cudaFree)
+# ------------------------------------------------------------------------------------------------
+def workspace_reserve(like=None, *, nbytes=None, iterations=10, FISTA=True, host_arrays=True, schedule=None,
+                      device=None) -> int:
+    """Make the library hold the device working set of later ``denoise3D`` / ``denoise4D`` calls.
+
+    Either ``nbytes`` or ``like`` (an array / tensor, or a ``(shape, dtype)`` pair) with the call's ``iterations``
+    / ``FISTA`` / ``schedule``; ``host_arrays``: the calls will pass NumPy arrays (input and result copies are part of
+    the working set).  Calls whose state fits carve the block up instead of allocating (~86 GB and 60 ms .. 0.7 s
+    per call for a 256x256x128x128 float32 cube); others allocate as before.  Returns the size in bytes.
+    ``workspace_release()`` gives the memory back.  Not part of the reference API (its state is NumPy arrays)."""
+    lib = _lib.load()
+    _lib.require_gpu()
+    if nbytes is None:
+        if like is None:
+            raise ValueError("workspace_reserve needs `like` or `nbytes`")
+        shape, dt = (like[0], np.dtype(like[1])) if isinstance(like, tuple) else (tuple(like.shape), _np_dtype(like))
+        if type(iterations) in (list, tuple):
+            nF, nU = int(iterations[0]), int(iterations[1])
+        else:
+            nF, nU = int(iterations * bool(FISTA)), int(iterations * (not FISTA))
+        P = DenoiseParams()
+        P.ndim, P.dtype = len(shape), _code(dt)
+        for k in range(len(shape)):
+            P.shape[k] = int(shape[k])
+        P.iters_fista, P.iters_plain, P.bc_mode = nF, nU, 2
+        P.schedule = {None: 0, "auto": 0, "two_pass": 1, "fused": 2}[schedule]
+        need = C.c_int64(0)
+        check(lib.cytvdn_denoise_workspace_bytes(C.byref(P), int(not host_arrays), int(not host_arrays), C.byref(need)))
+        nbytes = need.value
+    with _on_device(device):
+        check(lib.cytvdn_workspace_reserve(int(nbytes)))
+    return int(nbytes)
+
+
+def workspace_release(device=None) -> None:
+    """Free the block ``workspace_reserve`` holds on the (current) device."""
+    lib = _lib.load()
+    with _on_device(device):
+        check(lib.cytvdn_workspace_release())
+
+
+# ------------------------------------------------------------------------------------------------
 # drivers
 # ------------------------------------------------------------------------------------------------
 def _fmt_bytes(n) -> str:
@@ -312,7 +361,7 @@ def _as_host_vector(x, name):
 
 
 def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, isotropic_R, isotropic_Q,
-             reference_data, BC_mode, lam, quiet, out, timing, schedule=None):
+             reference_data, BC_mode, lam, quiet, out, timing, schedule=None, devices=None):
     lib = _lib.load()
     torch_in = _is_torch(datacube)
     dt = _np_dtype(datacube)
@@ -379,6 +428,22 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
             raise ValueError("torch input must be a CUDA tensor (pass a NumPy array for host data)")
         device = datacube.device.index if datacube.device.index is not None else torch.cuda.current_device()
         P.stream = torch.cuda.current_stream(datacube.device).cuda_stream
+        if out is not None:
+            # the library writes prod(shape) elements of the input's dtype through this pointer
+            if not (_is_torch(out) and out.is_cuda):
+                raise ValueError("out must be a CUDA tensor when datacube is one")
+            if out.device != datacube.device:
+                raise ValueError(f"out lives on {out.device}, datacube on {datacube.device}")
+            if out.dtype != datacube.dtype:
+                raise ValueError(f"out has dtype {out.dtype}, datacube {datacube.dtype}")
+            if tuple(out.shape) != tuple(datacube.shape):
+                raise ValueError(f"out has shape {tuple(out.shape)}, datacube {tuple(datacube.shape)}")
+            if not out.is_contiguous():
+                raise ValueError("out must be contiguous")
+            lo, hi = out.data_ptr(), out.data_ptr() + out.numel() * out.element_size()
+            dlo, dhi = datacube.data_ptr(), datacube.data_ptr() + datacube.numel() * datacube.element_size()
+            if lo < dhi and dlo < hi:
+                raise ValueError("out must not overlap datacube (the input is read in every iteration)")
         recon = out if out is not None else torch.empty_like(datacube)
         data_p, recon_p = datacube.data_ptr(), recon.data_ptr()
         keep = None
@@ -393,7 +458,11 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
             ref_p = None
     else:
         recon = out if out is not None else np.empty_like(datacube)
-        assert recon.flags["C_CONTIGUOUS"] and recon.dtype == dt and recon.shape == datacube.shape
+        if not (isinstance(recon, np.ndarray) and recon.flags["C_CONTIGUOUS"] and recon.dtype == dt
+                and recon.shape == datacube.shape and recon.flags["WRITEABLE"]):
+            raise ValueError("out must be a writeable C-contiguous NumPy array with the dtype and shape of datacube")
+        if np.shares_memory(recon, datacube):
+            raise ValueError("out must not overlap datacube (the input is read in every iteration)")
         data_p, recon_p = datacube.ctypes.data, recon.ctypes.data
         if reference_data is not None:
             keep = np.ascontiguousarray(reference_data, dtype=dt)
@@ -418,15 +487,29 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
     ms = (C.c_double * (n + 1))()
     done = (C.c_int32 * 3)()
     tm = (C.c_double * 3)()
-    with _on_device(device):
-        check(lib.cytvdn_denoise(C.byref(P), _vp(data_p), _vp(recon_p), _vp(ref_p), bn, dl,
-                                 ms if reference_data is not None else None, done, tm))
+    if devices is not None:
+        # several GPUs from this one process: scan-axis shards, halo planes pushed by the copy engines (cytvdn_shard.cu)
+        devs = [int(d) for d in devices]
+        if torch_in or reference_data is not None:
+            raise ValueError("devices=[...] takes a NumPy datacube (host arrays in and out) and no reference_data")
+        check(lib.cytvdn_denoise_sharded(C.byref(P), len(devs), (C.c_int * len(devs))(*devs), _vp(data_p), _vp(recon_p),
+                                         bn, dl, done, tm))
+    else:
+        with _on_device(device):
+            check(lib.cytvdn_denoise(C.byref(P), _vp(data_p), _vp(recon_p), _vp(ref_p), bn, dl,
+                                     ms if reference_data is not None else None, done, tm))
     if timing is not None:
+        cnt = C.c_int(0)
+        tms, tws = (C.c_double * 12)(), (C.c_char_p * 12)()
+        check(lib.cytvdn_last_trace(tms, tws, 12, C.byref(cnt)))
+        timing["trace_ms"] = ({tws[k].decode(): round(tms[k], 3) for k in range(min(cnt.value, 12))}
+                              if devices is None else {})
+        timing["devices"] = (int(done[2]) >> 8) if devices is not None else 1
         timing.update(setup_ms=tm[0], loop_ms=tm[1], finish_ms=tm[2], iters_fista=int(done[0]),
                       iters_plain=int(done[1]),
                       schedule={1: "two_pass", 2: "fused", 3: "streamed"}.get(int(done[2]) & 0xff, "none"),
-                      pipeline_boxes=(int(done[2]) >> 8) if (int(done[2]) & 0xff) != 3 else 0,
-                      stream_tiles=(int(done[2]) >> 8) if (int(done[2]) & 0xff) == 3 else 0)
+                      pipeline_boxes=(int(done[2]) >> 8) if ((int(done[2]) & 0xff) != 3 and devices is None) else 0,
+                      stream_tiles=(int(done[2]) >> 8) if ((int(done[2]) & 0xff) == 3 and devices is None) else 0)
     with np.errstate(all="ignore"):
         b_norm = np.array(bn[:n], dtype=np.float64).astype(dt)
         delta_recon = np.array(dl[:n], dtype=np.float64).astype(dt)
@@ -441,7 +524,7 @@ def _denoise(ndim, datacube, mu, iterations, FISTA, stopping_relative_change, is
 
 def denoise4D(datacube, mu, iterations=10, FISTA=True, stopping_relative_change=None, isotropic_R=False,
               isotropic_Q=False, reference_data=None, BC_mode=2, lam=None, quiet=False, *, out=None, timing=None,
-              schedule=None):
+              schedule=None, devices=None):
     """Proximal (an)isotropic TV denoising of a 4-D datacube on the GPU.
 
     Drop-in for ``cyTVDN.denoise4D`` (`cyTVDN/cyTVDN.py:19-247`): same arguments in the same order,
@@ -457,16 +540,27 @@ def denoise4D(datacube, mu, iterations=10, FISTA=True, stopping_relative_change=
     arrays), ``"two_pass"`` (96 B/voxel, in place) or ``None``: fused when it applies and fits in memory.
     ``"streamed"``: out of core -- host arrays larger than the GPU's memory are iterated tile by tile (temporal
     blocking over PCIe, `DESIGN.md` section 4); chosen automatically when nothing else fits.
-    All schedules give bit-identical results.
+    All schedules give bit-identical results.  ``devices=[0, 1, ...]``: shard scan axis 0 of a NumPy datacube over
+    several GPUs from this process (the C ABI's ``cytvdn_denoise_sharded``, the counterpart of `cyTVDN/mpi.py`:
+    anisotropic, ``BC_mode`` 2 or 0; ``schedule="streamed"`` runs shards larger than the GPUs out of core); the
+    result equals the single-GPU one bit for bit.
+
+    Early stopping (``stopping_relative_change``): ``delta_recon[i]`` is compared with the threshold exactly as in
+    `cyTVDN.py:189-194`, but it is computed from float64 sums.  The reference accumulates ``delta`` in the array
+    dtype, sequentially per OpenMP thread; in float32 that is off by 0.1 % .. 90 % for >= 4 M voxels and depends on
+    the thread count, so on large float32 inputs the reference may stop at another iteration
+    than this function (compare reconstructions at equal iteration counts).  Small arrays and float64 stop alike.
     """
     return _denoise(4, datacube, mu, iterations, FISTA, stopping_relative_change, isotropic_R, isotropic_Q,
-                    reference_data, BC_mode, lam, quiet, out, timing, schedule)
+                    reference_data, BC_mode, lam, quiet, out, timing, schedule, devices)
 
 
 def denoise3D(datacube, mu, iterations=7_500, stopping_relative_change=None, BC_mode=2, FISTA=False,
               reference_data=None, lam=None, quiet=False, *, out=None, timing=None, schedule=None):
     """Drop-in for ``cyTVDN.denoise3D`` (`cyTVDN/cyTVDN.py:250-435`).  Note the positional order
-    differs from ``denoise4D`` exactly as in the reference."""
+    differs from ``denoise4D`` exactly as in the reference.  Early stopping compares a float64-accumulated ``delta``
+    with the threshold (see ``denoise4D``): on large float32 cubes the reference's own float32 sums can make it stop
+    at another iteration."""
     return _denoise(3, datacube, mu, iterations, FISTA, stopping_relative_change, False, False,
                     reference_data, BC_mode, lam, quiet, out, timing, schedule)
 

@@ -70,6 +70,10 @@ int         cytvdn_device_count(int *count);
  *  zero_wrap_mask (reconstruction update only): bit k set -> the forward neighbour of the
  *            last index on axis k is taken as 0 instead of reading index 0 (tile on the
  *            global upper edge that holds a received plane at index 0).
+ *  flags bit 1 : (fused iteration only) store recon_out only for voxels inside the owned range; overlap planes of
+ *            recon are then written by the halo exchange alone (cytvdn_shard_*).
+ *  flags bits 4, 5 : (fused iteration only) half-isotropic update of the pair (0,1) / (2,3), i.e. isotropic_R /
+ *            isotropic_Q of cyTVDN.py:159-180; 4-D arrays, rows 16-byte aligned, Jia-Zhao on the pair's axes.
  *  flags bit 0 : hand the tiles of the sweep out dynamically (one global counter) instead of a static
  *            stride per CTA.  Use it for a sweep that overlaps with other GPU work (the NCCL halo exchange):
  *            the CTAs that are resident then share all tiles.  ~2 % slower when the kernel runs alone.
@@ -89,7 +93,7 @@ typedef struct cytvdn_step_opts {
     int64_t own_lo[2];
     int64_t own_hi[2];
     int32_t zero_wrap_mask;
-    int32_t flags;              /* bit 0: dynamic tile scheduling, bits 8..11: per-axis Jia-Zhao (see below) */
+    int32_t flags;              /* bit 0 dynamic tiles, 1 owned-only recon stores, 4/5 iso pairs, 8..11 per-axis Jia-Zhao */
     int64_t l2_budget_bytes;
     int64_t row_pitch;          /* elements between consecutive rows of the fast axis; 0 = dense (= extent) */
     /* cytvdn_fused_iteration only: axis-0 halo read from neighbouring GPUs through peer pointers
@@ -156,8 +160,9 @@ int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void
  * (= cytvdn_accumulator_update_all followed by cytvdn_datacube_update, bit-identical results, i.e. the
  * loop body cyTVDN.py:159-184 / :378-390).  Each array crosses HBM once: 76 B/voxel instead of 96
  * (4-D FISTA fp32).  OUT OF PLACE: the new state goes to recon_out / b_out / d_out, which must not
- * alias the inputs (forward neighbours are recomputed from the old state).  Anisotropic only;
- * bc_mode 0 or 2.  d_in == d_out == NULL -> unaccelerated.
+ * alias the inputs (forward neighbours are recomputed from the old state).  Anisotropic, or -- opts->flags bits
+ * 4 / 5 -- half-isotropic pairs (halfisotropic.pyx:63-95, :146-186); bc_mode 0 or 2.  d_in == d_out == NULL ->
+ * unaccelerated.
  * sums_dev[0] = sum |b_new| over all axes, [1] = sum |recon_out - recon_in|, [2] = sum |recon_in|.
  */
 int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void *orig,
@@ -189,7 +194,7 @@ typedef struct cytvdn_denoise_params {
     double  lambda_mu[4];       /* lam/mu             (cyTVDN.py:78) */
     int32_t device;             /* device to run on when `data` is a host pointer; -1 = current */
     int32_t schedule;           /* 0 auto, 1 two passes per iteration (in place), 2 fused single pass
-                                   (out of place, second set of b/d arrays; anisotropic only), 3 out of core
+                                   (out of place, second set of b/d arrays; not for bc_mode 3), 3 out of core
                                    (host arrays, tiles streamed over PCIe; see cytvdn_denoise) */
     void   *stream;             /* NULL = default stream */
 } cytvdn_denoise_params;
@@ -232,9 +237,29 @@ int cytvdn_denoise(const cytvdn_denoise_params *params, const void *data, void *
                    const void *reference_data, double *bnorm, double *delta, double *mse,
                    int32_t *iters_done, double *timing_ms);
 
-/* Device working set of cytvdn_denoise in bytes (GPU analogue of check_memory, cyTVDN.py:438). */
+/* Device working set of cytvdn_denoise in bytes (GPU analogue of check_memory, cyTVDN.py:438): every array the
+   call allocates for the schedule `params` asks for (0 = auto counts the fused schedule when it applies), padding
+   and reduction scratch included -- the number to hand to cytvdn_workspace_reserve. */
 int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *params, int data_on_device,
                                    int recon_on_device, int64_t *bytes);
+
+/*
+ * Optional reservation of the device working set (no counterpart in the reference, whose state lives in NumPy
+ * arrays the driver allocates per call, cyTVDN.py:127-145).  cytvdn_denoise allocates its state (up to 19 arrays,
+ * ~86 GB for BASELINE config 3) at entry and frees it at exit; on B200 that pair costs 60 ms to 0.7 s of host time.
+ * A caller that denoises repeatedly reserves once: the library then holds ONE block of `bytes` on the current
+ * device and every later call on that device whose state fits carves it up instead of calling cudaMalloc (calls
+ * that do not fit allocate as before).  reserve(bytes) grows an existing block if needed (never shrinks);
+ * release() frees it together with the per-stream reduction scratch.  Both fail with CYTVDN_E_INVALID while a call
+ * is using the block.  info: size of the block and how much of it is handed out right now.
+ */
+int cytvdn_workspace_reserve(int64_t bytes);
+int cytvdn_workspace_release(void);
+int cytvdn_workspace_info(int64_t *reserved_bytes, int64_t *in_use_bytes);
+
+/* Host-clock milestones (ms since entry) of the calling thread's last cytvdn_denoise and their labels (static
+   strings): where the wall time outside the CUDA events went.  *count = number recorded (<= 12). */
+int cytvdn_last_trace(double *ms, const char **what, int capacity, int *count);
 
 /*
  * Host-side plans of the two PCIe schedules of cytvdn_denoise (pure functions, no GPU needed; the call runs exactly
@@ -255,6 +280,99 @@ int cytvdn_denoise_workspace_bytes(const cytvdn_denoise_params *params, int data
 int cytvdn_pipeline_schedule(int nbox, int n_iter, int32_t *box, int32_t *iter, int64_t capacity,
                              int64_t *count);
 int cytvdn_stream_plan(const cytvdn_denoise_params *params, int64_t budget_bytes, int64_t *out8);
+
+/*
+ * ---------------------------------------------------------------------------------------------------------------
+ * Sharded loop: scan-axis shards over several GPUs.  Replaces the hot path of the reference's MPI driver,
+ * cyTVDN/mpi.py:130-210 (partition: tiles of ceil(N/w) planes with one overlap plane per neighbour, :161-196),
+ * :265-294 (exchange buffers) and :314-438 (iteration with a plane exchange after each half-step).
+ *
+ * 1-D split of scan axis 0 (contiguous halo planes, two neighbours; the reference's 2-D (wx, wy) grid stays
+ * available in the Python layer over NCCL), fused single-pass schedule, 4-D anisotropic, BC_mode 2 (mpi.py:84) or --
+ * `periodic` -- 0 with the wrap done by the exchange.  One cytvdn_shard per GPU.  Per iteration a shard sweeps its
+ * halo planes first, then its COPY ENGINES push the new first / last owned recon plane into the neighbours' overlap
+ * planes through peer pointers (same process: cudaDeviceEnablePeerAccess; one process per GPU: CUDA IPC) while the
+ * interior is swept; a 4-byte copy behind each plane raises a flag the neighbour's next iteration waits for.  No
+ * NCCL, no SM is spent on the exchange, no host synchronisation inside the loop.  Deviations from mpi.py that make
+ * the sharded result equal the single-GPU one bit for bit: the first / last OWNED planes
+ * travel (mpi.py:325,344,408,414 send the overlap planes), a shard on the global upper edge takes its wrap term
+ * as 0, FISTA is supported (mpi.py:310-311 is not), and bnorm / delta exist: sums over OWNED voxels.
+ *
+ * Use (every rank, or a loop over the ranks in one process):
+ *   create -> export -> [exchange the 128-byte handles] -> connect(0, lower's handle), connect(1, upper's handle)
+ *   -> load(block) -> iterate(nF, nU) [-> iterate ...] -> sums / store -> [all ranks synchronised] -> destroy.
+ * All ranks must enqueue the same iterations.  A shard may be re-loaded and re-run any number of times; all ranks
+ * must have finished (cytvdn_shard_synchronize + a barrier of the caller's) before any of them is destroyed.
+ * ---------------------------------------------------------------------------------------------------------------
+ */
+typedef struct cytvdn_shard cytvdn_shard;
+typedef struct cytvdn_shard_params {
+    int32_t dtype;              /* CYTVDN_F32 / CYTVDN_F64 */
+    int32_t world, rank;        /* tiles along scan axis 0 (mpi.py:130-150 with wy = 1) / this tile (mpi.py:156) */
+    int32_t periodic;           /* 0: Jia-Zhao (BC_mode 2), 1: periodic (BC_mode 0, first and last tile are neighbours) */
+    int32_t fista;              /* allocate the FISTA auxiliaries d */
+    int32_t max_iters;          /* iterations per load the shard keeps sums for */
+    int32_t device;             /* CUDA device, -1 = current */
+    int32_t reserved;
+    int64_t gshape[4];          /* GLOBAL array shape */
+    double  clip[4];            /* lambdaInv (mpi.py:249) */
+    double  lambda_mu[4];       /* lam / mu  (mpi.py:250) */
+} cytvdn_shard_params;
+
+int cytvdn_shard_create(const cytvdn_shard_params *params, cytvdn_shard **shard);
+int cytvdn_shard_destroy(cytvdn_shard *shard);
+/* out12 = { stored planes, first owned local plane, one past the last owned local plane, owned global range lo, hi,
+   global index of local plane 0 (-1 / wraps on a periodic axis), has lower neighbour, has upper neighbour, arena
+   bytes, row pitch in elements, kernels launched so far, iterations since the last load } */
+int cytvdn_shard_info(const cytvdn_shard *shard, int64_t out12[12]);
+/* 128-byte handle of this shard's device arena for its neighbours (CUDA IPC handle + layout; usable in the same
+   process too, where it resolves to the pointer itself) */
+int cytvdn_shard_export(const cytvdn_shard *shard, unsigned char handle[128]);
+/* side 0: the lower neighbour (rank-1), 1: the upper neighbour (rank+1); a no-op where there is no neighbour */
+int cytvdn_shard_connect(cytvdn_shard *shard, int side, const unsigned char handle[128]);
+/* block: the stored planes (owned + overlap: global planes [out12[5], out12[5] + out12[0])) with DENSE rows, host or
+   device pointer; NULL = the caller has written the shard's own `orig` array (cytvdn_shard_array) in place.
+   Resets accumulators, auxiliaries and the FISTA schedule (recon = datacube.copy(), mpi.py:247).  Asynchronous. */
+int cytvdn_shard_load(cytvdn_shard *shard, const void *block);
+/* enqueue n_fista FISTA iterations, then n_plain unaccelerated ones (returns at once) */
+int cytvdn_shard_iterate(cytvdn_shard *shard, int n_fista, int n_plain);
+/* wait for everything this shard has enqueued; reports a halo wait that timed out (dead neighbour) */
+int cytvdn_shard_synchronize(cytvdn_shard *shard);
+/* out[i*3 + {0,1,2}] = this shard's sum|b|, sum|recon' - recon|, sum|recon| over OWNED voxels of iteration i < n
+   (synchronises) */
+int cytvdn_shard_sums(cytvdn_shard *shard, double *out, int n);
+/* the owned planes of the current reconstruction, dense rows, to a host or device pointer (synchronous) */
+int cytvdn_shard_store(cytvdn_shard *shard, void *owned_block);
+/* device pointer of an internal array (rows `row pitch` apart): which 0 orig, 1 recon, 2 b[axis], 3 d[axis];
+   set 0 = the state the next iteration reads, 1 = the other state set */
+int cytvdn_shard_array(const cytvdn_shard *shard, int which, int set, int axis, void **ptr);
+int cytvdn_shard_streams(const cytvdn_shard *shard, void **compute_stream, void **copy_stream);
+/* per-phase CUDA events for the first 256 iterations after a load; timeline: out[i*6 + k] in ms, k = 0 start of
+   iteration i since iteration 0, 1 wait for the neighbours' planes, 2 halo planes, 3 interior sweep, 4 halo done ->
+   first push issued (copy-stream latency), 5 pushes (copy engines; overlaps 3) */
+int cytvdn_shard_profile(cytvdn_shard *shard, int on);
+int cytvdn_shard_timeline(cytvdn_shard *shard, double *out, int n);
+
+/*
+ * The whole sharded run from ONE process: `ndev` devices (devices[r], or 0..ndev-1 when NULL) each take a tile of
+ * scan axis 0 of the HOST (or managed) arrays `data` -> `recon`; same parameters and outputs as cytvdn_denoise
+ * (4-D, anisotropic, BC_mode 2 or 0, schedule 0/2 in core, 3 = out of core: see cytvdn_denoise_sharded_streamed).
+ * Bit-identical to cytvdn_denoise on one GPU.  iters_done[2] = schedule | ndev << 8.
+ */
+int cytvdn_denoise_sharded(const cytvdn_denoise_params *params, int ndev, const int *devices, const void *data,
+                           void *recon, double *bnorm, double *delta, int32_t *iters_done, double *timing_ms);
+/*
+ * Sharded AND out of core: arrays whose state does not fit the GPUs' memory together (BASELINE config 5 on 2 or 4
+ * GPUs; README.md:104-120 of the reference: "data larger than memory").  The out-of-core schedule of
+ * cytvdn_denoise (temporal blocking: tiles of axis-0 planes + K halo planes are iterated K times per pass, state
+ * between passes in page-locked host arrays) with the tiles of every pass dealt to `ndev` devices, one host thread
+ * per device.  The K halo planes a device's first / last tile needs from the neighbouring device's range are read
+ * from the host arrays before any device writes its results of the pass back (a barrier per pass instead of a halo
+ * exchange per iteration).  Host arrays in and out, BC_mode 2, fixed iteration counts.  Bit-identical to the
+ * in-core schedules.  budget_bytes_per_device: 0 = what is free on each device.
+ */
+int cytvdn_denoise_sharded_streamed(const cytvdn_denoise_params *params, int ndev, const int *devices, const void *data,
+                                    void *recon, double *bnorm, double *delta, int32_t *iters_done, double *timing_ms);
 
 /*
  * Deterministic synthetic 4D-STEM-like counts for benchmarks and sharded parity runs

@@ -178,10 +178,15 @@ def test_c_abi_argument_validation_without_gpu():
     n = C.c_int64(0)
     P.ndim, P.isotropic_R, P.iters_fista, P.iters_plain = 4, 0, 10, 0
     assert lib.cytvdn_denoise_workspace_bytes(C.byref(P), 1, 1, C.byref(n)) == 0
-    assert n.value == (8 * 2 + 1) * 4 * 256            # fused: two b/d sets + the second recon buffer
+    scratch = ((11 * 4 * 16 * 8 + 255) // 256) * 256 + 8192    # reduction slots of 10 iterations (+ MSE[0])
+    assert n.value == (8 * 2 + 1) * 4 * 256 + scratch   # fused: two b/d sets + the second recon buffer
     P.schedule = 1
     assert lib.cytvdn_denoise_workspace_bytes(C.byref(P), 0, 0, C.byref(n)) == 0
-    assert n.value == (8 + 2) * 4 * 256                # two-pass from host data: b, d, orig, recon
+    assert n.value == (8 + 2) * 4 * 256 + scratch       # two-pass from host data: b, d, orig, recon
+    # the optional reservation needs a device: without one it reports the CUDA error instead of crashing
+    cnt = C.c_int(0)
+    lib.cytvdn_denoise(C.byref(P), None, None, None, None, None, None, None, None)
+    assert lib.cytvdn_last_trace(None, None, 0, C.byref(cnt)) == 0 and cnt.value == 0
     assert lib.cytvdn_launch_count() >= 0
 
 
