@@ -195,13 +195,13 @@ def run_sharded(args):
             # events on the engine's compute stream (torch.cuda.Event would see torch's current stream only)
             cs = torch.cuda.ExternalStream(eng_streams(eng)[0], device=dev)
             if args.timeline:
-                eng.load(None)                                # profiling counts from a load; warm-up is done
+                eng.load(None)                                # per-phase events count from a load: warm up again
                 dist.barrier()
+                eng.profile(True)
                 for _ in range(args.warmup):
                     eng.iterate(1, 0)
                 eng.synchronize()
                 dist.barrier()
-                eng.profile(True)
         else:
             cs = torch.cuda.current_stream(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

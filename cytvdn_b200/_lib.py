@@ -35,6 +35,7 @@ class StepOpts(C.Structure):
         ("peer_hi_recon", C.c_void_p),
         ("peer_hi_b0", C.c_void_p),
         ("peer_hi_d0", C.c_void_p),
+        ("sse_reference", C.c_void_p),
     ]
 
 

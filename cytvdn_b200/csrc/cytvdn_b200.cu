@@ -414,26 +414,28 @@ int run_dcu(const Dims &D, const void *orig, const void *uin, void *uout, const 
     const int vw = pick_vw<T>(D.pitch, pb);
     if (int rc = make_sweep(D, vw, sizeof(T), opts, 2 + D.ndim, &P.S)) return rc;
     P.f = (const T *)orig; P.uin = (const T *)uin; P.uout = (T *)uout;
+    P.ref = opts ? (const T *)opts->sse_reference : nullptr;
     Workspace ws;
     if (int rc = get_workspace(st, &ws)) return rc;
     P.W.partials = ws.partials; P.W.ticket = ws.ticket; P.W.out = sums_dev;
     if (P.S.ntiles <= 0) {
-        CUDA_TRY(cudaMemsetAsync(sums_dev, 0, 2 * sizeof(double), st));
+        CUDA_TRY(cudaMemsetAsync(sums_dev, 0, (P.ref ? 3 : 2) * sizeof(double), st));
         return CYTVDN_OK;
     }
+    if (P.ref && vw != vec_width<T>())
+        return fail(CYTVDN_E_UNSUPPORTED, "sse_reference needs 16-byte aligned rows (use cytvdn_sum_square_error otherwise)");
     if (int rc = dispatch_vw<T>(vw, [&](auto VWc) -> int {
             constexpr int VW = decltype(VWc)::value;
             int grid = 1;
-            if (D.ndim == 4) {
-                auto k = tv_datacube_kernel<T, VW, true>;
+            auto go = [&](auto k) -> int {
                 if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
                 k<<<grid, kBlock, 0, st>>>(P);
-            } else {
-                auto k = tv_datacube_kernel<T, VW, false>;
-                if (int rc = grid_for(k, P.S.ntiles, &grid)) return rc;
-                k<<<grid, kBlock, 0, st>>>(P);
+                return CYTVDN_OK;
+            };
+            if constexpr (VW == vec_width<T>()) {
+                if (P.ref) return D.ndim == 4 ? go(tv_datacube_kernel<T, VW, true, true>) : go(tv_datacube_kernel<T, VW, false, true>);
             }
-            return CYTVDN_OK;
+            return D.ndim == 4 ? go(tv_datacube_kernel<T, VW, true>) : go(tv_datacube_kernel<T, VW, false>);
         }))
         return rc;
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -470,6 +472,7 @@ struct FusedCall {
     int bc[4];
     bool fista;
     int iso_mask;                                // bit 0: pair (0,1), bit 1: pair (2,3) half-isotropic
+    bool mirror;                                 // BC_mode 3 (all axes)
     double tk;
     int zero_wrap;
     double *sums_dev;
@@ -505,11 +508,22 @@ int run_fused(const FusedCall &c)
     P.f = (const T *)c.orig; P.uin = (const T *)c.uin; P.uout = (T *)c.uout;
     P.tk = (T)c.tk; P.zero_wrap = c.zero_wrap;
     P.lo_u = (const T *)c.lo_u; P.hi_u = (const T *)c.hi_u; P.hi_b0 = (const T *)c.hi_b0; P.hi_d0 = (const T *)c.hi_d0;
+    P.ref = c.opts ? (const T *)c.opts->sse_reference : nullptr;
+    if (c.mirror) {
+        if (!vec || c.iso_mask || c.lo_u || c.hi_u || P.ref)
+            return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=3 in the fused iteration: anisotropic, 16-byte aligned rows, no peer "
+                                              "pointers, no sse_reference (the two-pass kernels cover the rest)");
+        for (int k = 0; k < 4; ++k)
+            if ((c.D.ndim == 4 || k != 2) && c.D.n[k] < 2) return fail(CYTVDN_E_INVALID, "mirror boundary needs extent >= 2 on every axis");
+    }
+    if (P.ref && (c.iso_mask || !vec || c.lo_u || c.hi_u))
+        return fail(CYTVDN_E_UNSUPPORTED, "sse_reference in the fused iteration: anisotropic, 16-byte aligned rows, no peer "
+                                          "pointers (use cytvdn_sum_square_error otherwise)");
     Workspace ws;
     if (int rc = get_workspace(c.st, &ws)) return rc;
     P.W.partials = ws.partials; P.W.ticket = ws.ticket; P.W.out = c.sums_dev;
     if (P.S.ntiles <= 0) {
-        CUDA_TRY(cudaMemsetAsync(c.sums_dev, 0, 3 * sizeof(double), c.st));
+        CUDA_TRY(cudaMemsetAsync(c.sums_dev, 0, (P.ref ? 4 : 3) * sizeof(double), c.st));
         return CYTVDN_OK;
     }
     int grid = 1;
@@ -563,6 +577,16 @@ int run_fused(const FusedCall &c)
                 k<<<grid, kBlock, 0, c.st>>>(P);
                 return CYTVDN_OK;
             };
+            if constexpr (VW == vec_width<T>()) {
+                if (c.mirror) {                                 // BC_mode 3
+                    if (c.fista) return ax2 ? go(tv_fused_kernel<T, VW, true, true, false, false, true>) : go(tv_fused_kernel<T, VW, true, false, false, false, true>);
+                    return ax2 ? go(tv_fused_kernel<T, VW, false, true, false, false, true>) : go(tv_fused_kernel<T, VW, false, false, false, false, true>);
+                }
+                if (P.ref) {                                    // sum (ref - recon')^2 in the same pass
+                    if (c.fista) return ax2 ? go(tv_fused_kernel<T, VW, true, true, false, true>) : go(tv_fused_kernel<T, VW, true, false, false, true>);
+                    return ax2 ? go(tv_fused_kernel<T, VW, false, true, false, true>) : go(tv_fused_kernel<T, VW, false, false, false, true>);
+                }
+            }
             auto pick = [&](auto PEERc) -> int {
                 constexpr bool PEER = decltype(PEERc)::value;
                 if (c.fista) return ax2 ? go(tv_fused_kernel<T, VW, true, true, PEER>) : go(tv_fused_kernel<T, VW, true, false, PEER>);
@@ -706,9 +730,10 @@ int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void
     if (bc_mode == 1)
         return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=1 (mirror) is undefined behaviour in the reference's "
                                           "datacube_update (utils.pyx:117-120) and is not implemented");
-    if (bc_mode == 3)
-        return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=3 (clamped mirror) runs on the two-pass schedule only");
-    if (bc_mode != 0 && bc_mode != 2) return fail(CYTVDN_E_INVALID, "BC_mode must be 0 or 2");
+    if (bc_mode != 0 && bc_mode != 2 && bc_mode != 3) return fail(CYTVDN_E_INVALID, "BC_mode must be 0, 2 or 3");
+    c.mirror = bc_mode == 3;
+    if (c.mirror && opts && ((opts->flags >> 8) & 15))
+        return fail(CYTVDN_E_UNSUPPORTED, "per-axis Jia-Zhao overrides (flags bits 8..11) do not combine with BC_mode=3");
     c.iso_mask = opts ? ((opts->flags >> 4) & 3) : 0;
     if (c.iso_mask && ndim != 4) return fail(CYTVDN_E_INVALID, "half-isotropic update exists for 4-D only");
     for (int k = 0; k < ndim; ++k) {
@@ -796,7 +821,7 @@ namespace {
 // 1 = two passes (96 B/voxel, in place).  params->schedule: 0 auto, 1, 2; env CYTVDN_SCHEDULE overrides.
 bool fused_possible(const cytvdn_denoise_params *p)
 {
-    return p->bc_mode == 0 || p->bc_mode == 2;      // anisotropic and half-isotropic; the mirror (3) runs two-pass
+    return p->bc_mode == 0 || p->bc_mode == 2 || p->bc_mode == 3;    // (the mirror is anisotropic only: validate_params)
 }
 int requested_schedule(const cytvdn_denoise_params *p)
 {
@@ -1281,7 +1306,7 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
                 o.box_hi[0] = e1 < n0 ? np - (k + 1) : np;
                 o.own_lo[0] = c0 - e0;
                 o.own_hi[0] = c1 - e0;
-                if (e1 == n0 && e0 > 0) o.zero_wrap_mask = 1;   // plane 0 of b_0 is identically 0 under Jia-Zhao
+                if (e1 == n0 && e0 > 0 && p->bc_mode == 2) o.zero_wrap_mask = 1;   // plane 0 of b_0 is identically 0 under Jia-Zhao
                 const bool fi = m < nF;
                 const void *uin = (first && k == 0) ? sl.f : sl.r;      // recon = datacube.copy(), cyTVDN.py:145
                 double *sm = sums_d + ((size_t)m * nt + t) * 4;
@@ -1400,7 +1425,8 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         bool want = requested_schedule(p) == 3;
         size_t budget = 0;
         { const char *env = getenv("CYTVDN_STREAM_BUDGET_MB"); if (env && atof(env) > 0) { budget = (size_t)(atof(env) * 1048576.0); want = true; } }
-        const bool can = !data_on_dev && !recon_on_dev && p->bc_mode == 2 && !p->use_stopping && !reference_data && nIt > 0;
+        const bool can = !data_on_dev && !recon_on_dev && (p->bc_mode == 2 || p->bc_mode == 3) && !p->use_stopping &&
+                         !reference_data && nIt > 0;
         size_t free_b = 0;
         // (cudaMemGetInfo costs 15 - 20 ms on a B200 with tens of GB allocated: asked only when the answer matters)
         if (want || (can && requested_schedule(p) == 0)) if (int rc = available_bytes(&free_b)) return rc;
@@ -1410,7 +1436,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         }
         if (want) {
             if (!can)
-                return fail(CYTVDN_E_UNSUPPORTED, "the out-of-core schedule needs host arrays in and out, BC_mode 2, at "
+                return fail(CYTVDN_E_UNSUPPORTED, "the out-of-core schedule needs host arrays in and out, BC_mode 2 or 3, at "
                                                   "least one iteration, no stopping test and no reference_data");
             if (!budget) budget = free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : free_b / 2;
             return denoise_streamed(p, D, data, recon, bnorm, delta, iters_done, timing_ms, budget);
@@ -1422,14 +1448,19 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     {
         const int want = requested_schedule(p);
         if (want == 2 && !fused_possible(p))
-            return fail(CYTVDN_E_INVALID, "the fused schedule does not cover the mirror boundary (BC_mode 3); use "
-                                          "schedule 0 or 1");
+            return fail(CYTVDN_E_INVALID, "the fused schedule does not cover this boundary mode; use schedule 0 or 1");
         // The pair (0,1) costs the fused kernel three joint shrinks per voxel instead of one (the forward
         // neighbours on both far axes are recomputed): measured on config 4, 20.6 ms fused against 16.5 ms in two
         // passes; (2,3) alone is a wash (16.1 / 16.3 ms).  Auto therefore runs isotropic_R in two passes.
         const bool fused_pays = !p->isotropic_R;
+        // the mirror variant of the fused kernel exists for the full vector width only
+        const bool mirror_ok = p->bc_mode != 3 || (n3p % full_vw == 0 &&
+                                                   (!data_dev || (reinterpret_cast<uintptr_t>(data) & 15u) == 0) &&
+                                                   (!recon_dev || (reinterpret_cast<uintptr_t>(recon) & 15u) == 0));
+        if (want == 2 && !mirror_ok)
+            return fail(CYTVDN_E_UNSUPPORTED, "BC_mode=3 on the fused schedule needs 16-byte aligned rows and arrays");
         if (want == 2 && nIt > 0) fused = true;                 // asked for: an allocation failure is reported, not hidden
-        else if (want != 1 && fused_possible(p) && fused_pays && nIt > 0) {
+        else if (want != 1 && fused_possible(p) && fused_pays && mirror_ok && nIt > 0) {
             size_t free_b = 0;
             if (int rc = available_bytes(&free_b)) return rc;
             const int64_t need = arrays_needed(p, true, data_dev, recon_dev, reference_data && !ref_dev) * (int64_t)nb;
@@ -1447,8 +1478,14 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     // counts (no stopping test, no per-iteration MSE: both need the whole array at one iteration).
     // The last box takes its wrap term as 0 (zero_wrap): plane 0 of b_0 is identically 0 under Jia-Zhao.
     int nbox = 1;
+    // sum (reference - recon')^2 can ride along in the pass that produces recon' when that kernel has the variant:
+    // full vector width (rows and caller pointers 16-byte aligned), and not the fused half-isotropic kernel
+    auto aligned16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool sse_in_pass = reference_data && !(fused && (p->isotropic_R || p->isotropic_Q || p->bc_mode == 3)) && n3p % full_vw == 0 &&
+                             (!data_dev || aligned16(data)) && (!recon_dev || aligned16(recon)) &&
+                             (!ref_dev || aligned16(reference_data));
     {
-        const bool can = fused && p->bc_mode == 2 && !p->use_stopping && !reference_data && nIt > 0 &&
+        const bool can = fused && (p->bc_mode == 2 || p->bc_mode == 3) && !p->use_stopping && (!reference_data || sse_in_pass) && nIt > 0 &&
                          (!data_on_dev || !recon_on_dev);
         int want = nb >= ((size_t)256 << 20) ? 16 : 1;
         const char *env = getenv("CYTVDN_PIPELINE");
@@ -1595,8 +1632,9 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
         return p->dtype == CYTVDN_F32 ? run_sse<float>(nvox, a, b, out, st, n3, n3p)
                                       : run_sse<double>(nvox, a, b, out, st, n3, n3p);
     };
-    if (reference_data)
-        if (int rc = sse(orig_d, ref_d, sums_d + (size_t)nIt * 4 * nbox + 3)) return rc;
+    // MSE[i+1] = sum (reference - recon_{i+1})^2 rides along in the pass that produces recon_{i+1} (fused kernel /
+    // half-step B) unless that kernel has no such variant (fused half-isotropic): then it is a sweep of its own
+    if (sse_in_pass) sopts.sse_reference = ref_d;
 
     CUDA_TRY(cudaEventRecord(ev[1], st));
     // iteration 0 reads the reconstruction straight from the input (recon = datacube.copy(),
@@ -1638,7 +1676,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
                     return rc;
             }
             u_cur = u_out;
-            if (reference_data)
+            if (reference_data && !sse_in_pass)
                 if (int rc = sse(ref_d, u_cur, s + 3)) return rc;
             ran[i] = 1;
             ++done[phase];
@@ -1677,7 +1715,7 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
             cytvdn_step_opts o = sopts;
             if (c >= 0) {
                 o.box_lo[0] = box_lo(c); o.box_hi[0] = box_lo(c + 1);
-                if (c == nbox - 1) o.zero_wrap_mask |= 1;
+                if (c == nbox - 1 && p->bc_mode == 2) o.zero_wrap_mask |= 1;    // (mirror: the last plane's term is b' - b')
             }
             const bool fi = m < nF;
             const int in = m & 1, out = in ^ 1;
@@ -1711,6 +1749,8 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
             CUDA_TRY(cudaStreamWaitEvent(st, side.down[0], 0));
         }
     }
+    if (reference_data)                        // MSE[0] = sum (datacube - reference)^2 (cyTVDN.py:122-125); the input is
+        if (int rc = sse(orig_d, ref_d, sums_d + (size_t)nIt * 4 * nbox + 3)) return rc;      // complete on the device by now
     if (recon_dev && u_cur != rbuf[0])         // zero iterations, or the fused ping-pong ended in the spare buffer
         CUDA_TRY(cudaMemcpyAsync(rbuf[0], u_cur, nb, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaEventRecord(ev[2], st));

@@ -95,7 +95,7 @@ struct cytvdn_shard {
     int dtype = 0, world = 1, rank = 0, device = 0;
     size_t elem = 4;
     int64_t g[4] = {0, 0, 0, 0};
-    bool periodic = false, has_lo = false, has_hi = false;
+    bool periodic = false, mirror = false, has_lo = false, has_hi = false;
     int64_t valid_lo = 0, valid_hi = 0;       // owned global planes [lo, hi)
     int64_t read_lo = 0;                      // global index of local plane 0 (may be -1 -> wraps when periodic)
     int64_t n_local = 0, own_lo = 0, own_hi = 0;
@@ -205,14 +205,14 @@ int enqueue_iteration(cytvdn_shard *s, bool fista_it)
     o.own_lo[0] = s->own_lo; o.own_hi[0] = s->own_hi;
     o.flags = 2;                                              // recon is stored for owned voxels only
     if (s->periodic && s->world > 1) o.flags |= 1 << 8;       // the wrap of axis 0 is the exchange's job
-    if (!s->periodic && s->has_lo && !s->has_hi) o.zero_wrap_mask = 1;   // global upper edge
+    if (!s->periodic && !s->mirror && s->has_lo && !s->has_hi) o.zero_wrap_mask = 1;   // global upper edge
     auto sweep = [&](int64_t lo, int64_t hi, int slot) -> int {
         if (hi <= lo) return CYTVDN_OK;
         cytvdn_step_opts ob = o;
         ob.box_lo[0] = lo; ob.box_hi[0] = hi;
         ++s->launches;
         return cytvdn_fused_iteration(4, shape, s->dtype, s->array(0), uin, uout, bin, bout, fista_it ? din : nullptr,
-                                      fista_it ? dout : nullptr, tkr, s->clip, s->w, s->periodic ? 0 : 2, sums + slot * 4,
+                                      fista_it ? dout : nullptr, tkr, s->clip, s->w, s->periodic ? 0 : (s->mirror ? 3 : 2), sums + slot * 4,
                                       &ob, s->comp);
     };
     CYTVDN_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * kSlots * 4, s->comp));
@@ -274,7 +274,7 @@ int cytvdn_shard_create(const cytvdn_shard_params *p, cytvdn_shard **out)
                     (long long)p->gshape[0], p->world, (long long)n, p->rank);
     cytvdn_shard *s = new cytvdn_shard();
     s->dtype = p->dtype; s->elem = p->dtype == CYTVDN_F32 ? 4 : 8;
-    s->world = p->world; s->rank = p->rank; s->periodic = p->periodic != 0;
+    s->world = p->world; s->rank = p->rank; s->periodic = p->periodic == 1; s->mirror = p->periodic == 2;
     for (int k = 0; k < 4; ++k) { s->g[k] = p->gshape[k]; s->clip[k] = p->clip[k]; s->w[k] = p->lambda_mu[k]; }
     s->fista = p->fista != 0; s->max_iters = p->max_iters;
     plan_1d(s);
@@ -562,7 +562,8 @@ int cytvdn_denoise_sharded(const cytvdn_denoise_params *p, int ndev, const int *
     if (ndev < 1 || ndev > 64) return fail(CYTVDN_E_INVALID, "ndev must be in 1..64");
     if (p->ndim != 4) return fail(CYTVDN_E_UNSUPPORTED, "sharding exists for 4-D datacubes only (mpi.py:252-255)");
     if (p->isotropic_R || p->isotropic_Q) return fail(CYTVDN_E_UNSUPPORTED, "the sharded loop is anisotropic (mpi.py:317-358)");
-    if (p->bc_mode != 0 && p->bc_mode != 2) return fail(CYTVDN_E_UNSUPPORTED, "sharded runs support BC_mode 2 (mpi.py:84) and 0");
+    if (p->bc_mode != 0 && p->bc_mode != 2 && p->bc_mode != 3)
+        return fail(CYTVDN_E_UNSUPPORTED, "sharded runs support BC_mode 2 (mpi.py:84), 0 and 3");
     const int nF = p->iters_fista, nU = p->iters_plain, nIt = nF + nU;
     if (nF < 0 || nU < 0) return fail(CYTVDN_E_INVALID, "negative iteration count");
     if (nIt > 0 && (!bnorm || !delta)) return fail(CYTVDN_E_INVALID, "bnorm / delta is NULL");
@@ -584,7 +585,8 @@ int cytvdn_denoise_sharded(const cytvdn_denoise_params *p, int ndev, const int *
     } cleanup{sh};
     cytvdn_shard_params sp;
     memset(&sp, 0, sizeof sp);
-    sp.dtype = p->dtype; sp.world = ndev; sp.periodic = p->bc_mode == 0; sp.fista = nF > 0; sp.max_iters = std::max(1, nIt);
+    sp.dtype = p->dtype; sp.world = ndev; sp.periodic = p->bc_mode == 0 ? 1 : (p->bc_mode == 3 ? 2 : 0);
+    sp.fista = nF > 0; sp.max_iters = std::max(1, nIt);
     for (int k = 0; k < 4; ++k) { sp.gshape[k] = p->shape[k]; sp.clip[k] = p->clip[k]; sp.lambda_mu[k] = p->lambda_mu[k]; }
     std::vector<std::array<unsigned char, 128>> handles(ndev);
     for (int r = 0; r < ndev; ++r) {

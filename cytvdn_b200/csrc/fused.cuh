@@ -37,7 +37,8 @@ struct FusedParams {
     const T *hi_u;
     const T *hi_b0;
     const T *hi_d0;
-    RedWork W;            // out[0] = sum|b'|, out[1] = sum|recon' - recon|, out[2] = sum|recon|
+    const T *ref;         // reference_data (cyTVDN.py:186-187) or nullptr; SSE instantiations only
+    RedWork W;            // out[0] = sum|b'|, out[1] = sum|recon' - recon|, out[2] = sum|recon| (, out[3] = sum (ref - recon')^2)
 };
 
 // v = clip((u - p) + b);  b' = v + tk (v - d)   (anisotropic.pyx:46-54, :127-132)
@@ -50,7 +51,12 @@ __device__ __forceinline__ void acc_update(T u, T p, T b, T d, T clip, T tk, T &
 
 // PEER: axis-0 halo planes may live on a neighbouring GPU (pointer selects; costs ~2 % when compiled in, so the
 // single-GPU / NCCL schedules use the PEER=false instantiation)
-template <typename T, int VW, bool FISTA, bool AX2, bool PEER>
+// SSE: also accumulate sum (reference - recon')^2 (sum_square_error_*, utils.pyx:14-49; MSE[i+1] of cyTVDN.py:186-187)
+// in the same pass: one more streamed read, no extra sweep.
+// MIRROR: BC_mode 3 on every axis (this repo's well-defined mirror, include/cytvdn_b200.h): the backward neighbour of
+// index 0 is index 1 (anisotropic.pyx:69-70) and the forward index of the last voxel is clamped (utils.pyx:117-120
+// with min instead of max), i.e. that axis' divergence term is w * (b' - b') there.
+template <typename T, int VW, bool FISTA, bool AX2, bool PEER, bool SSE = false, bool MIRROR = false>
 #ifndef FUSED_MINB
 #define FUSED_MINB 2
 #endif
@@ -73,7 +79,7 @@ tv_fused_kernel(const FusedParams<T> P)
     // All reads keep the default L2 policy: marking the last-use ("self") loads evict-first was measured
     // 25 % slower -- inside a wave a neighbour may still need the line.
     auto ld_self = [&](const T *p) -> Vec<T, VW> { return ld_ro<T, VW>(p); };
-    double acc[3] = {0.0, 0.0, 0.0};
+    double acc[SSE ? 4 : 3] = {};
     constexpr int NFAR = AX2 ? 3 : 2;                 // far axes 0, 1 (, 2)
 
     TileSched sched{P.W.ticket + 1, S.dynamic, 0};
@@ -94,7 +100,8 @@ tv_fused_kernel(const FusedParams<T> P)
         for (int d = 0; d < NFAR; ++d) {
             const int64_t span = (int64_t)(extent[d] - 1) * stride[d];
             // backward neighbour; at index 0: itself (Jia-Zhao, difference 0) or the last index (periodic)
-            poff[d] = coord[d] != 0 ? e - stride[d] : (P.bc[d] == 2 ? e : e + span);
+            if (MIRROR) poff[d] = coord[d] != 0 ? e - stride[d] : e + stride[d];
+            else poff[d] = coord[d] != 0 ? e - stride[d] : (P.bc[d] == 2 ? e : e + span);
             at_end[d] = coord[d] == extent[d] - 1;
             yoff[d] = at_end[d] ? e - span : e + stride[d];          // forward neighbour (wraps to index 0)
         }
@@ -138,8 +145,10 @@ const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
             by[d] = ld_ro_ordered<T, VW>(d == 0 ? by0_ptr : P.bin[d] + yoff[d]);
             if (FISTA) dy[d] = ld_ro_ordered<T, VW>(d == 0 ? dy0_ptr : P.din[d] + yoff[d]);
         }
-        if (c.l0 == 0) left = (P.bc[3] == 2) ? us.v[0] : __ldg(P.uin + e + (S.n3 - 1));
-        else if (lane == 0) left = __ldg(P.uin + e - 1);
+        if (c.l0 == 0) {
+            if (MIRROR) left = VW > 1 ? us.v[VW > 1 ? 1 : 0] : __ldg(P.uin + e + 1);
+            else left = (P.bc[3] == 2) ? us.v[0] : __ldg(P.uin + e + (S.n3 - 1));
+        } else if (lane == 0) left = __ldg(P.uin + e - 1);
         Vec<T, VW> v3, n3s;      // clipped value and new accumulator of this thread's voxels, axis 3
 #pragma unroll
         for (int v = 0; v < VW; ++v)
@@ -148,7 +157,7 @@ const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
         T right3 = __shfl_down_sync(0xffffffffu, n3s.v[0], 1);     // b'_3 of the next voxel on the row
         T wrap3 = T(0);                     // b'_3 beyond the row's last voxel: the row's voxel 0 (or 0)
         if (c.row_end) {
-            if (!(P.zero_wrap & 8)) {
+            if (!(P.zero_wrap & 8) && !MIRROR) {
                 const int64_t y = e - c.l0;
                 const T uyy = __ldg(P.uin + y);
                 T ulast = us.v[0];                           // the row's last real voxel lives in this vector
@@ -176,7 +185,7 @@ const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
         for (int v = 0; v < VW; ++v) {
             if (v <= c.vl) sb += absval(n3s.v[v]);           // pad voxels of a padded row do not count
             T fwd = v == VW - 1 ? right3 : n3s.v[v + 1 < VW ? v + 1 : v];
-            if (c.row_end && v == c.vl) fwd = wrap3;
+            if (c.row_end && v == c.vl) fwd = MIRROR ? n3s.v[v] : wrap3;
             term[3].v[v] = P.w[3] * (n3s.v[v] - fwd);
         }
 
@@ -195,6 +204,7 @@ const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
                 acc_update<T, FISTA>(uy[d].v[v], jz0 ? uy[d].v[v] : us.v[v], by[d].v[v], FISTA ? dy[d].v[v] : T(0),
                                      P.clip[d], P.tk, vy, nf);
                 if (zero) nf = T(0);
+                if (MIRROR && at_end[d]) nf = ns.v[v];
                 if (v <= c.vl) sb += absval(ns.v[v]);
                 term[d].v[v] = P.w[d] * (ns.v[v] - nf);
             }
@@ -224,8 +234,16 @@ const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
             acc[1] += (double)sd;
             acc[2] += (double)so;
         }
+        if (SSE) {
+            const Vec<T, VW> rf = ld_stream<T, VW>(P.ref + e);
+            if (c.owned) {
+#pragma unroll
+                for (int v = 0; v < VW; ++v)
+                    if (v <= c.vl) { const T t = rf.v[v] - un.v[v]; acc[SSE ? 3 : 0] += (double)(t * t); }
+            }
+        }
     }
-    reduce_finish<3>(acc, P.W);
+    reduce_finish<SSE ? 4 : 3>(acc, P.W);
 }
 
 // ------------------------------------------------------------------------------------------------------------

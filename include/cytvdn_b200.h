@@ -23,8 +23,8 @@
  *    (utils.pyx:117-120 take the forward index as max(i+1, N-1)) and is rejected here.
  *    bc_mode 3 (CYTVDN_BC_MIRROR, NOT in the reference) is the well-defined reading of those lines:
  *    accumulator update as bc_mode 1, reconstruction update with the forward index CLAMPED,
- *    min(i+1, N-1), i.e. the term of an axis vanishes at its last index.  Anisotropic only,
- *    two-pass schedule only, every extent >= 2.
+ *    min(i+1, N-1), i.e. the term of an axis vanishes at its last index.  Anisotropic only, every extent >= 2;
+ *    all schedules (two-pass, fused, PCIe pipeline, out of core, sharded).
  *  - Per-voxel arithmetic is bit-identical to the reference (separately rounded mul/add,
  *    IEEE division, comparison-based clip); only the reductions differ: they are
  *    accumulated in float64 (the reference's array-dtype sums are inaccurate).
@@ -104,6 +104,10 @@ typedef struct cytvdn_step_opts {
     const void *peer_hi_recon;
     const void *peer_hi_b0;
     const void *peer_hi_d0;
+    /* cytvdn_fused_iteration (anisotropic) and cytvdn_datacube_update: device array of the arrays' shape and row
+       pitch; when set, sum (sse_reference - recon_out)^2 over the owned voxels is written behind the other sums
+       (sums_dev[3] / sums_dev[2]) -- sum_square_error_* (utils.pyx:14-49) of cyTVDN.py:186-187 folded into the pass. */
+    const void *sse_reference;
 } cytvdn_step_opts;
 
 /*
@@ -161,8 +165,8 @@ int cytvdn_datacube_update(int ndim, const int64_t *shape, int dtype, const void
  * loop body cyTVDN.py:159-184 / :378-390).  Each array crosses HBM once: 76 B/voxel instead of 96
  * (4-D FISTA fp32).  OUT OF PLACE: the new state goes to recon_out / b_out / d_out, which must not
  * alias the inputs (forward neighbours are recomputed from the old state).  Anisotropic, or -- opts->flags bits
- * 4 / 5 -- half-isotropic pairs (halfisotropic.pyx:63-95, :146-186); bc_mode 0 or 2.  d_in == d_out == NULL ->
- * unaccelerated.
+ * 4 / 5 -- half-isotropic pairs (halfisotropic.pyx:63-95, :146-186); bc_mode 0, 2 or (anisotropic, rows 16-byte
+ * aligned) 3.  d_in == d_out == NULL -> unaccelerated.
  * sums_dev[0] = sum |b_new| over all axes, [1] = sum |recon_out - recon_in|, [2] = sum |recon_in|.
  */
 int cytvdn_fused_iteration(int ndim, const int64_t *shape, int dtype, const void *orig,
@@ -187,7 +191,7 @@ typedef struct cytvdn_denoise_params {
     int32_t iters_plain;        /* ... then unaccelerated ones (cyTVDN.py:98-108) */
     int32_t isotropic_R;        /* 4-D only */
     int32_t isotropic_Q;        /* 4-D only */
-    int32_t bc_mode;            /* 0, 2 or 3 (3: anisotropic, runs two-pass) */
+    int32_t bc_mode;            /* 0, 2 or 3 (3: anisotropic only) */
     int32_t use_stopping;       /* stop a phase when delta < stopping_relative_change */
     double  stopping_relative_change;
     double  clip[4];            /* lambdaInv = 1/lam  (cyTVDN.py:77) */
@@ -309,7 +313,8 @@ typedef struct cytvdn_shard cytvdn_shard;
 typedef struct cytvdn_shard_params {
     int32_t dtype;              /* CYTVDN_F32 / CYTVDN_F64 */
     int32_t world, rank;        /* tiles along scan axis 0 (mpi.py:130-150 with wy = 1) / this tile (mpi.py:156) */
-    int32_t periodic;           /* 0: Jia-Zhao (BC_mode 2), 1: periodic (BC_mode 0, first and last tile are neighbours) */
+    int32_t periodic;           /* 0: Jia-Zhao (BC_mode 2), 1: periodic (BC_mode 0, first and last tile are neighbours),
+                                   2: the clamped mirror (BC_mode 3) at the global edges */
     int32_t fista;              /* allocate the FISTA auxiliaries d */
     int32_t max_iters;          /* iterations per load the shard keeps sums for */
     int32_t device;             /* CUDA device, -1 = current */

@@ -57,6 +57,14 @@ def one_device():
         print(json.dumps({"case": [list(shape), world, iters, periodic, dtype], "engine": ok1, "c_loop": ok2,
                           "ok": ok1 and ok2}), flush=True)
         bad += not (ok1 and ok2)
+    # BC_mode=3 (clamped mirror) sharded: the mirror applies at the global edges only
+    data = make((14, 6, 8, 12), "float32", 9)
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = tv.denoise4D(data, mu, [7, 3], True, BC_mode=3, quiet=True, schedule="two_pass")
+    out = tv.denoise4D(data, mu, [7, 3], True, BC_mode=3, quiet=True, devices=[0, 0, 0])
+    ok = bool(np.array_equal(out[0], ref[0])) and np.allclose(out[2], ref[2], rtol=1e-4)
+    print(json.dumps({"case": "BC_mode=3 sharded", "ok": ok}), flush=True)
+    bad += not ok
     # early stopping through the single-process loop: stops where the single-GPU loop stops
     data = make((12, 8, 8, 16), "float32", 5)
     mu = np.array([1, 1, .5, .5], dtype=np.float32)
@@ -81,6 +89,7 @@ def ipc(share_gpu):
     dist.init_process_group("gloo" if share_gpu else "nccl", rank=rank, world_size=world,
                             **({} if share_gpu else {"device_id": torch.device("cuda", local)}))
     bad = 0
+    fdev = "cpu" if share_gpu else "cuda"                # gloo reduces host tensors, NCCL device tensors
     try:
         for shape, _, iters, periodic, dtype in cases_small():
             if shape[0] < world:
@@ -95,7 +104,7 @@ def ipc(share_gpu):
             ok = bool(np.array_equal(own.cpu().numpy(), ref[0][plan.owned_global[0]])) and \
                 np.allclose(dl.astype(np.float64), ref[2].astype(np.float64), rtol=1e-4)
             # early stopping: every rank stops at the single-GPU iteration
-            flag = torch.tensor([int(ok)])
+            flag = torch.tensor([int(ok)], device=fdev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if rank == 0:
                 print(json.dumps({"case": [list(shape), world, iters, periodic, dtype], "ok": bool(flag.item())}), flush=True)
@@ -109,7 +118,7 @@ def ipc(share_gpu):
         block = torch.from_numpy(np.ascontiguousarray(plan.extract(data))).cuda()
         own, bn, dl = sharded.denoise4D_engine(block, mu, [30, 4], True, thr, gshape=data.shape)
         ok = bool(np.array_equal(own.cpu().numpy(), ref[0][plan.owned_global[0]])) and np.array_equal(dl != 0, ref[2] != 0)
-        flag = torch.tensor([int(ok)])
+        flag = torch.tensor([int(ok)], device=fdev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             print(json.dumps({"case": "early stop (hybrid)", "ok": bool(flag.item())}), flush=True)

@@ -165,8 +165,10 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 1
     assert "anisotropic update only" in err()
     P.isotropic_Q, P.schedule = 0, 2
-    assert lib.cytvdn_fused_iteration(4, sh4, 0, one, one, one, bp, bp, None, None, 0.0, w, w, 3, one, None, None) == 4
-    assert "two-pass" in err()
+    assert lib.cytvdn_fused_iteration(4, sh4, 0, one, one, one, bp, bp, None, None, 0.0, w, w, 3, one, None, None) == 1
+    assert "out of place" in err()                      # BC_mode 3 is accepted by the fused iteration (round 2)
+    assert lib.cytvdn_fused_iteration(4, sh4, 0, one, one, one, bp, bp, None, None, 0.0, w, w, 4, one, None, None) == 1
+    assert "BC_mode must be 0, 2 or 3" in err()
     P.schedule = 0
     P.shape[2] = 1
     assert lib.cytvdn_denoise(C.byref(P), one, two, None, None, None, None, None, None) == 1

@@ -132,12 +132,15 @@ def test_gpu_mirror_denoise_equals_oracle(tv, shape, dt, iters, fista, pad, monk
     mu = np.array([1, 1, .5, .5] if len(shape) == 4 else [1, 1, .5], dtype=dt)
     fn, ofn = (tv.denoise4D, O.denoise4D) if len(shape) == 4 else (tv.denoise3D, O.denoise3D)
     want = ofn(x, mu, iters, FISTA=fista, BC_mode=3, quiet=True, kernels=O.PortKernels("D"), scalars="D")
-    tm = {}
-    got = fn(x, mu, iters, FISTA=fista, BC_mode=3, quiet=True, timing=tm)
-    assert tm["schedule"] == "two_pass"
-    assert np.array_equal(got[0], want[0]), float(np.abs(got[0] - want[0]).max())
-    np.testing.assert_allclose(got[1].astype(np.float64), want[1], rtol=1e-6)
-    np.testing.assert_allclose(got[2].astype(np.float64), want[2], rtol=1e-6)
+    vec_rows = pad == "1" or shape[-1] % (4 if dt == "float32" else 2) == 0
+    for sched in (None, "two_pass"):
+        tm = {}
+        got = fn(x, mu, iters, FISTA=fista, BC_mode=3, quiet=True, timing=tm, schedule=sched)
+        # auto: the fused kernel's mirror variant wherever rows are 16-byte aligned (padded internally by default)
+        assert tm["schedule"] == ("fused" if (sched is None and vec_rows) else "two_pass"), (tm, sched)
+        assert np.array_equal(got[0], want[0]), (sched, float(np.abs(got[0] - want[0]).max()))
+        np.testing.assert_allclose(got[1].astype(np.float64), want[1], rtol=1e-6)
+        np.testing.assert_allclose(got[2].astype(np.float64), want[2], rtol=1e-6)
 
 
 @pytest.mark.gpu
@@ -155,9 +158,33 @@ def test_gpu_mirror_step_function_and_errors(tv):
     assert r == pytest.approx(float(np.abs((want - old).astype(np.float64)).sum() / np.abs(old.astype(np.float64)).sum()),
                               rel=1e-9)
     mu = np.array([1, 1, .5, .5], dtype=np.float32)
-    with pytest.raises(Exception, match="two-pass|fused schedule"):
-        tv.denoise4D(f, mu, 3, True, BC_mode=3, quiet=True, schedule="fused")
+    a = tv.denoise4D(f, mu, 3, True, BC_mode=3, quiet=True, schedule="fused")      # round 2: the fused kernel knows the mirror
+    b = tv.denoise4D(f, mu, 3, True, BC_mode=3, quiet=True, schedule="two_pass")
+    assert np.array_equal(a[0], b[0])
     with pytest.raises(Exception, match="anisotropic update only"):
         tv.denoise4D(f, mu, 3, True, isotropic_Q=True, BC_mode=3, quiet=True)
     with pytest.raises(NotImplementedError, match="BC_mode=3"):
         tv.denoise4D(f, mu, 3, True, BC_mode=1, quiet=True)
+
+
+@pytest.mark.gpu
+def test_gpu_mirror_pipelined_and_streamed(tv, monkeypatch):
+    """BC_mode=3 outside the plain loop (round-1 review): PCIe pipeline and out-of-core tiles give the in-core
+    single-GPU result bit for bit."""
+    rng = np.random.default_rng(8)
+    x = counts(rng, (24, 6, 8, 16), "float32")
+    mu = np.array([1, 1, .5, .5], dtype=np.float32)
+    ref = tv.denoise4D(x, mu, [9, 4], True, BC_mode=3, quiet=True, schedule="two_pass")
+    monkeypatch.setenv("CYTVDN_PIPELINE", "5")
+    tm = {}
+    got = tv.denoise4D(x, mu, [9, 4], True, BC_mode=3, quiet=True, timing=tm)
+    assert tm["schedule"] == "fused" and tm["pipeline_boxes"] == 5
+    assert np.array_equal(got[0], ref[0])
+    monkeypatch.delenv("CYTVDN_PIPELINE")
+    plane = 6 * 8 * 16 * 4
+    monkeypatch.setenv("CYTVDN_STREAM_BUDGET_MB", str(10 * 2.5 * 12 * plane / 1048576.0))
+    tm = {}
+    got = tv.denoise4D(x, mu, [9, 4], True, BC_mode=3, quiet=True, timing=tm)
+    assert tm["schedule"] == "streamed" and tm["stream_tiles"] > 1
+    assert np.array_equal(got[0], ref[0])
+    # (axis-0 shards with BC_mode=3: tests/engine_driver.py, run by tests/test_shard_engine.py in its own process)

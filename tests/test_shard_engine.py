@@ -31,7 +31,7 @@ def test_engine_all_ranks_on_one_device():
     (`tv.denoise4D(devices=[0, 0, ...])`) -- uneven splits, one plane per rank, odd rows, periodic, hybrid counts,
     float64, early stopping."""
     lines = _run([sys.executable, DRIVER, "one_device"])
-    assert len(lines) == 10
+    assert len(lines) == 11
 
 
 @pytest.mark.gpu
