@@ -439,6 +439,7 @@ def main():
                          "round 1's torch.distributed schedules (N > 1)")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the parity checks over the process group")
     ap.add_argument("--no-alone", action="store_true", help="N > 1: skip the single-GPU run of one shard's shape")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling point of config 5 itself")
     ap.add_argument("--timeline", default=None, help="N > 1: write per-phase CUDA-event timings of the timed steps here")
     ap.add_argument("--timeline-full", action="store_true", help="keep every iteration of every rank in the timeline file")
     args = ap.parse_args()

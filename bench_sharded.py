@@ -349,6 +349,59 @@ def run_sharded(args):
                 alone["efficiency_like_for_like"] = ms1 / ms_per_step
             dist.barrier()
 
+        # ---- strong scaling of BASELINE config 5 itself (the fixed 1024x1024x128x128 array, 69 GB raw) ------------
+        # 8 GPUs: the main line above IS config 5 (fused, 19 arrays = 166 GB per GPU).  4 GPUs: 258 planes per GPU do not
+        # fit the fused schedule's second state set, but the in-place two-pass schedule does (10 arrays = 173 GB of the
+        # 192 GB): run it here over NCCL.  2 GPUs: the state (687 GB) exceeds the two GPUs' HBM (384 GB); the out-of-core
+        # schedule (cytvdn_denoise_sharded_streamed) would need 687 GB of page-locked host memory for the state between
+        # passes -- stated, not run, when the box does not have it.
+        strong = None
+        full = (1024, 1024, 128, 128)
+        if not args.shape and not args.no_strong:
+            if world == 8:
+                strong = {"n_gpus": 8, "shape": list(full), "schedule": schedule, "value": value, "ms_per_step": ms_per_step,
+                          "note": "the main line of this run"}
+            elif world == 4:
+                try:
+                    if eng is not None:
+                        close_engine(eng)
+                        eng = None
+                    torch.cuda.empty_cache()
+                    plan5 = sharded.ShardPlan(full, world, rank)
+                    x5 = synth.stem4d_device(full, offset0=plan5.read[0][0], lshape0=plan5.local_shape[0], seed=2, counts=500.0, device=dev)
+                    sh5 = sharded.CudaShard(plan5, x5, mu, None, fista=True, n_iter=args.warmup + args.steps, fused=False)
+                    tk5, it5 = 1.0, 0
+                    for k in range(args.warmup + args.steps):
+                        if k == args.warmup:
+                            torch.cuda.synchronize()
+                            dist.barrier()
+                            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            s0.record()
+                        tkr5, tk5 = sharded.fista_ratio(tk5)
+                        sharded._run_iteration_overlapped(sh5, it5, tkr5, True, None, comm_stream)
+                        it5 += 1
+                    s1.record()
+                    torch.cuda.synchronize()
+                    t5 = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+                    g5 = sh5.local_sums().clone()
+                    dist.all_reduce(g5)
+                    l5 = g5[it5 - 1].cpu().numpy()
+                    strong = {"n_gpus": 4, "shape": list(full), "schedule": "two_pass (in place, 10 arrays = 173 GB per GPU; NCCL halo exchange)",
+                              "value": int(np.prod(full)) * args.steps / (float(t5[0]) * 1e-3) / 1e9,
+                              "ms_per_step": float(t5[0]) / args.steps, "delta_last": float(l5[1] / l5[2])}
+                    del sh5, x5
+                    torch.cuda.empty_cache()
+                except Exception as ex:
+                    strong = {"n_gpus": 4, "shape": list(full), "error": repr(ex)[:300]}
+            elif world == 2:
+                from bench import mem_available_gb
+                strong = {"n_gpus": 2, "shape": list(full), "feasible": False,
+                          "why": "state of config 5 = 10 arrays x 68.7 GB = 687 GB; 2 GPUs hold 384 GB of HBM, so only the "
+                                 "out-of-core schedule applies (cytvdn_denoise_sharded_streamed), which keeps b and d in "
+                                 f"page-locked host memory between passes: 550 GB + 137 GB for data and result; this box has "
+                                 f"{mem_available_gb():.0f} GB.  tools/sharded_stream_bench.py runs that schedule at the largest "
+                                 "size the host holds (profiles/r2_sharded_stream_bench.jsonl)."}
         cpu = None
         if rank == 0 and not args.no_cpu:
             r_ = cpu_reference_run(5, 1, budget_s=15.0)
@@ -362,7 +415,8 @@ def run_sharded(args):
                                    {"workload": f"4-D FISTA fp32 sharded, {'x'.join(map(str, per))} per GPU (non-default)"},
                                    schedule=schedule),
                     "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches[0]),
-                    "clocks": clk, "check": check, "single_gpu_same_shard": alone, "timeline": timeline}
+                    "clocks": clk, "check": check, "single_gpu_same_shard": alone, "timeline": timeline,
+                    "strong_scaling_config5": strong}
             print(json.dumps(line), flush=True)
     finally:
         try:

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcytvdn_b200.so")
+LIB_PATH = os.environ.get("CYTVDN_LIB") or os.path.join(HERE, "libcytvdn_b200.so")     # CYTVDN_LIB: experimental builds
 
 F32, F64 = 0, 1
 OK = 0
@@ -123,6 +123,7 @@ PROTOTYPES = {
                                                   _dp, C.POINTER(C.c_int32), _dp]),
     "cytvdn_pipeline_schedule": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64, _i64p]),
     "cytvdn_stream_plan": (C.c_int, [C.POINTER(DenoiseParams), C.c_int64, _i64p]),
+    "cytvdn_stream_plan_sharded": (C.c_int, [C.POINTER(DenoiseParams), C.c_int64, C.c_int, _i64p]),
     "cytvdn_synth_counts": (C.c_int, [_i64p, C.c_int64, C.c_int64, C.c_int, _vp, _vp, C.c_double, C.c_uint64,
                                       _vp, _vp]),
     "cytvdn_malloc": (C.c_int, [_vpp, C.c_int64]),

@@ -187,6 +187,31 @@ __device__ __forceinline__ double ldg_nc_ordered(const double *p)
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
     return r;
 }
+// Ordering point for ONE warp: a named barrier that only this warp's 32 threads join (ids 1..8, one per warp of the
+// CTA), carrying a predicate computed from x.  It completes as soon as the warp arrives -- no waiting for the other
+// warps -- but it is a BAR instruction: ptxas moves no memory operation across it, and it cannot issue before x exists.
+// Round 2: replaces the CTA-wide __syncthreads_or of round 1 in the float kernels (12 % of the stall samples were
+// warps waiting at that barrier for the CTA's slowest warp; measured +2 % on config 3, +4 % 4-D unaccelerated, +6 %
+// config 1).  The float64 kernels keep the CTA barrier: with coherent self loads they spill (measured 34 -> 25).
+template <typename T> struct WarpOrder { static constexpr bool value = sizeof(T) == 4; };
+#ifdef CYTVDN_CTA_BARRIER_ORDER        // build knob: round 1's ordering everywhere
+template <> struct WarpOrder<float> { static constexpr bool value = false; };
+#endif
+__device__ __forceinline__ unsigned order_after(float x)
+{
+    unsigned r;
+    asm volatile("{ .reg .pred p, q; setp.neu.f32 q, %1, %1; barrier.red.or.pred p, %2, 32, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "f"(x), "r"(1u + (threadIdx.x >> 5)) : "memory");
+    return r;
+}
+__device__ __forceinline__ unsigned order_after(double x)
+{
+    unsigned r;
+    asm volatile("{ .reg .pred p, q; setp.neu.f64 q, %1, %1; barrier.red.or.pred p, %2, 32, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "d"(x), "r"(1u + (threadIdx.x >> 5)) : "memory");
+    return r;
+}
+
 template <typename T, int VW>
 __device__ __forceinline__ Vec<T, VW> ld_ro_ordered(const T *p)
 {

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -987,7 +988,7 @@ struct StreamPlan {
     int64_t plane_bytes;       // one axis-0 plane of an internal (row-padded) array
     int64_t host_state_bytes;  // page-locked host arrays the call allocates (b, d between passes)
 };
-int make_stream_plan(const cytvdn_denoise_params *p, const Dims &D, size_t budget, StreamPlan *sp)
+int make_stream_plan(const cytvdn_denoise_params *p, const Dims &D, size_t budget, StreamPlan *sp, int ndev = 1)
 {
     const int nd = p->ndim, nF = p->iters_fista, M = p->iters_fista + p->iters_plain;
     const int64_t elem = p->dtype == CYTVDN_F32 ? 4 : 8, full_vw = 16 / elem;
@@ -996,16 +997,22 @@ int make_stream_plan(const cytvdn_denoise_params *p, const Dims &D, size_t budge
     sp->arrays_per_slot = 2 + nd * (nF > 0 ? 2 : 1);
     if (M <= 0) return fail(CYTVDN_E_INVALID, "the out-of-core schedule needs at least one iteration");
     int64_t P = (int64_t)(budget / ((size_t)2 * sp->arrays_per_slot * sp->plane_bytes));
-    if (P >= n0) { P = n0; sp->iters_per_pass = M; sp->core_planes = n0; }      // one tile: nothing is recomputed
+    if (ndev == 1 && P >= n0) { P = n0; sp->iters_per_pass = M; sp->core_planes = n0; }      // one tile: nothing is recomputed
     else {
-        // two slots of P planes + the carry buffer (2K = P/2 planes): 2.5 P planes of every array
-        P = (int64_t)(budget / ((size_t)5 * sp->arrays_per_slot * sp->plane_bytes / 2));
+        // two slots of P planes + the carry buffer (2K = P/2 planes): 2.5 P planes of every array; several devices
+        // additionally snapshot the K planes above their last tile (edge buffer): 2.75 P
+        P = ndev == 1 ? (int64_t)(budget / ((size_t)5 * sp->arrays_per_slot * sp->plane_bytes / 2))
+                      : (int64_t)(budget / ((size_t)11 * sp->arrays_per_slot * sp->plane_bytes / 4));
         if (P < 4)
             return fail(CYTVDN_E_NOMEM, "out-of-core schedule: two tiles of 4 planes and their carry buffer (%lld bytes) do "
                                         "not fit in the device budget of %zu bytes",
                         (long long)(10 * sp->arrays_per_slot * sp->plane_bytes), budget);
         sp->iters_per_pass = std::min<int64_t>(M, std::max<int64_t>(1, P / 4));     // P/4 minimises the traffic per iteration
         sp->core_planes = P - 2 * sp->iters_per_pass;
+        if (ndev > 1) {     // a multiple of ndev tiles of equal size, so that every device gets the same work
+            const int64_t per_dev = (n0 + (int64_t)ndev * sp->core_planes - 1) / ((int64_t)ndev * sp->core_planes);
+            sp->core_planes = std::max<int64_t>(1, (n0 + per_dev * ndev - 1) / (per_dev * ndev));
+        }
     }
     sp->planes_per_slot = P;
     sp->tiles = (n0 + sp->core_planes - 1) / sp->core_planes;
@@ -1114,13 +1121,36 @@ struct HostPinned {
     }
 };
 
-int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *data, void *recon, double *bnorm,
-                     double *delta, int32_t *iters_done, double *timing_ms, size_t budget)
+// What the devices of one out-of-core run share: the tile geometry, the host state between passes, the per-tile sums
+// and a barrier (one host thread per device; a single device never waits).
+struct StreamShared {
+    StreamPlan sp;
+    int ndev = 1;
+    void *hb[4] = {nullptr, nullptr, nullptr, nullptr}, *hd[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<double> sums_h;                       // [M][tiles][4]
+    // barrier; wait() returns false once any device has failed (everybody then unwinds)
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    uint64_t phase = 0;
+    bool failed = false;
+    bool wait()
+    {
+        if (ndev == 1) return !failed;
+        std::unique_lock<std::mutex> lk(mu);
+        if (failed) return false;
+        if (++arrived == ndev) { arrived = 0; ++phase; cv.notify_all(); return true; }
+        const uint64_t ph = phase;
+        cv.wait(lk, [&] { return phase != ph || failed; });
+        return !failed;
+    }
+    void fail_all() { std::lock_guard<std::mutex> lk(mu); failed = true; cv.notify_all(); }
+};
+
+// One device's share of the out-of-core schedule: tiles [t_lo, t_hi) of every pass.
+int stream_worker(const cytvdn_denoise_params *p, const Dims &D, const void *data, void *recon, StreamShared &sh, int t_lo, int t_hi,
+                  cudaStream_t user_stream)
 {
-    const auto t_start = std::chrono::steady_clock::now();
-    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    };
     const int nd = p->ndim, nF = p->iters_fista, nU = p->iters_plain, M = nF + nU;
     const size_t elem = p->dtype == CYTVDN_F32 ? 4 : 8;
     const int64_t full_vw = 16 / (int64_t)elem;
@@ -1129,27 +1159,31 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
     const int64_t plane_rows = D.n[1] * D.n[2];
     const size_t plane_b = (size_t)plane_rows * n3p * elem;           // one plane of an internal array
     const bool fista = nF > 0;
-
-    // ---- tile geometry: P planes per slot, K iterations per pass, `core` = P - 2K planes advanced per tile ----
-    StreamPlan sp;
-    if (int rc = make_stream_plan(p, D, budget, &sp)) return rc;
+    const StreamPlan &sp = sh.sp;
     const int64_t P = sp.planes_per_slot, K = sp.iters_per_pass, core = sp.core_planes;
     const int nt = (int)sp.tiles;
-    const int npass = (int)sp.passes;
+    const int ntl = std::max(0, t_hi - t_lo);                         // tiles of this device
+    const bool multi = sh.ndev > 1;
+    void *const *hb = sh.hb, *const *hd = sh.hd;
 
     Arena pool;
     const size_t slot_b = (size_t)sp.arrays_per_slot * Arena::padded((size_t)P * plane_b);
-    const size_t nsums = (size_t)M * nt * 4;
+    const size_t nsums = (size_t)M * std::max(ntl, 1) * 4;
     // slot[2] is the CARRY buffer: the 2K planes two neighbouring tiles share are saved from tile t's slot before it
-    // starts iterating and handed to tile t+1, so that every plane crosses the bus once per pass
-    const int64_t carry_planes = nt > 1 ? 2 * K : 0;
+    // starts iterating and handed to tile t+1, so that every plane crosses the bus once per pass.
+    // slot[3] is the EDGE buffer (several devices only): the K planes above this device's last tile belong to the next
+    // device, which writes them back early in the pass -- they are snapshotted before any device writes anything.
+    const int64_t carry_planes = ntl > 1 ? 2 * K : 0;
+    const int64_t edge_planes = (multi && t_hi < nt && ntl > 0) ? K : 0;
     const size_t carry_b = (size_t)sp.arrays_per_slot * Arena::padded((size_t)carry_planes * plane_b);
-    if (int rc = pool.reserve(2 * slot_b + carry_b + Arena::padded(nsums * sizeof(double)) + 4096)) return rc;
-    struct Slot { void *f, *r, *b[4], *d[4]; } slot[3];
+    const size_t edge_b = (size_t)sp.arrays_per_slot * Arena::padded((size_t)edge_planes * plane_b);
+    if (ntl > 0)
+        if (int rc = pool.reserve(2 * slot_b + carry_b + edge_b + Arena::padded(nsums * sizeof(double)) + 4096)) return rc;
+    struct Slot { void *f, *r, *b[4], *d[4]; } slot[4];
     memset(slot, 0, sizeof slot);
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < 4 && ntl > 0; ++q) {
         Slot &sl = slot[q];
-        const size_t planes = q < 2 ? (size_t)P : (size_t)carry_planes;
+        const size_t planes = q < 2 ? (size_t)P : q == 2 ? (size_t)carry_planes : (size_t)edge_planes;
         if (planes == 0) continue;
         if (int rc = pool.alloc(&sl.f, planes * plane_b)) return rc;
         if (int rc = pool.alloc(&sl.r, planes * plane_b)) return rc;
@@ -1158,27 +1192,20 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
             if (fista) if (int rc = pool.alloc(&sl.d[k], planes * plane_b)) return rc;
         }
     }
-    Slot &carry = slot[2];
+    Slot &carry = slot[2], &edge = slot[3];
     double *sums_d = nullptr;
-    if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
-
-    // host state between passes (internal, padded layout); recon's host state is the caller's array
-    HostPinned hostmem;
-    void *hb[4] = {0, 0, 0, 0}, *hd[4] = {0, 0, 0, 0};
-    if (npass > 1)
-        for (int k = 0; k < nd; ++k) {
-            if (int rc = hostmem.alloc(&hb[k], (size_t)n0 * plane_b)) return rc;
-            if (fista && nF > K) if (int rc = hostmem.alloc(&hd[k], (size_t)n0 * plane_b)) return rc;
-        }
+    if (ntl > 0) if (int rc = pool.alloc((void **)&sums_d, nsums * sizeof(double))) return rc;
 
     struct Streams {
-        cudaStream_t up = nullptr, comp = nullptr, down = nullptr;      // comp is the caller's stream (not owned)
+        cudaStream_t up = nullptr, comp = nullptr, down = nullptr;      // comp may be the caller's stream (not owned)
+        bool own_comp = false;
         cudaEvent_t up_done[2] = {0, 0}, comp_done[2] = {0, 0}, down_done[2] = {0, 0};
         ~Streams()
         {
             // error paths leave copies in flight that reference the host state freed right after this object
             if (up) cudaStreamSynchronize(up);
             if (down) cudaStreamSynchronize(down);
+            if (comp && own_comp) cudaStreamSynchronize(comp);
             for (int q = 0; q < 2; ++q) {
                 if (up_done[q]) cudaEventDestroy(up_done[q]);
                 if (comp_done[q]) cudaEventDestroy(comp_done[q]);
@@ -1186,36 +1213,40 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
             }
             if (up) cudaStreamDestroy(up);
             if (down) cudaStreamDestroy(down);
+            if (comp && own_comp) cudaStreamDestroy(comp);
         }
     } S;
     CUDA_TRY(cudaStreamCreateWithFlags(&S.up, cudaStreamNonBlocking));
-    S.comp = (cudaStream_t)p->stream;                 // kernels run on the caller's stream (its reduction workspace is cached)
+    if (multi) { CUDA_TRY(cudaStreamCreateWithFlags(&S.comp, cudaStreamNonBlocking)); S.own_comp = true; }
+    else S.comp = user_stream;                        // kernels run on the caller's stream (its reduction workspace is cached)
     CUDA_TRY(cudaStreamCreateWithFlags(&S.down, cudaStreamNonBlocking));
     for (int q = 0; q < 2; ++q) {
         CUDA_TRY(cudaEventCreateWithFlags(&S.up_done[q], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&S.comp_done[q], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&S.down_done[q], cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaMemsetAsync(sums_d, 0, nsums * sizeof(double), S.comp));
-    CUDA_TRY(cudaStreamSynchronize(S.comp));
+    if (ntl > 0) {
+        CUDA_TRY(cudaMemsetAsync(sums_d, 0, nsums * sizeof(double), S.comp));
+        CUDA_TRY(cudaStreamSynchronize(S.comp));
+    }
 
     // planes [g0, g0 + np) of a dense caller array <-> planes [l0, ...) of an internal (padded) tile array
     auto dense_to_tile = [&](void *tile, int64_t l0, const void *host, int64_t g0, int64_t np, cudaStream_t st) -> int {
         if (np <= 0) return CYTVDN_OK;
         char *dp = (char *)tile + (size_t)l0 * plane_b;
-        const char *sp = (const char *)host + (size_t)g0 * plane_rows * n3 * elem;
-        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
+        const char *sp_ = (const char *)host + (size_t)g0 * plane_rows * n3 * elem;
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp_, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
         CUDA_TRY(cudaMemsetAsync(dp, 0, (size_t)np * plane_b, st));
-        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3p * elem, sp, (size_t)n3 * elem, (size_t)n3 * elem,
+        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3p * elem, sp_, (size_t)n3 * elem, (size_t)n3 * elem,
                                    (size_t)(np * plane_rows), cudaMemcpyDefault, st));
         return CYTVDN_OK;
     };
     auto tile_to_dense = [&](void *host, int64_t g0, const void *tile, int64_t l0, int64_t np, cudaStream_t st) -> int {
         if (np <= 0) return CYTVDN_OK;
         char *dp = (char *)host + (size_t)g0 * plane_rows * n3 * elem;
-        const char *sp = (const char *)tile + (size_t)l0 * plane_b;
-        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
-        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3 * elem, sp, (size_t)n3p * elem, (size_t)n3 * elem,
+        const char *sp_ = (const char *)tile + (size_t)l0 * plane_b;
+        if (!padded) { CUDA_TRY(cudaMemcpyAsync(dp, sp_, (size_t)np * plane_b, cudaMemcpyDefault, st)); return CYTVDN_OK; }
+        CUDA_TRY(cudaMemcpy2DAsync(dp, (size_t)n3 * elem, sp_, (size_t)n3p * elem, (size_t)n3 * elem,
                                    (size_t)(np * plane_rows), cudaMemcpyDefault, st));
         return CYTVDN_OK;
     };
@@ -1229,8 +1260,6 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
             tk = tk_new;
         }
     }
-    const double setup_ms = ms_since(t_start);
-    const auto t_loop = std::chrono::steady_clock::now();
 
     for (int pass = 0, m0 = 0; m0 < M; ++pass, m0 += (int)K) {
         const int Kp = (int)std::min<int64_t>(K, M - m0);
@@ -1239,23 +1268,31 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
         const bool need_d_out = fista && m0 + Kp < nF;          // ... and one of a later pass will
         auto ext_lo = [&](int t) { return std::max<int64_t>(0, (int64_t)t * core - Kp); };
         auto ext_hi = [&](int t) { return std::min<int64_t>(n0, std::min<int64_t>(n0, (int64_t)(t + 1) * core) + Kp); };
+        // planes of this device's last tile that lie above its core and belong to the next device
+        const bool use_edge = edge_planes > 0 && !first;
+        const int64_t edge_g0 = std::min<int64_t>(n0, (int64_t)t_hi * core);      // first plane of the next device
 
         auto upload = [&](int t) -> int {
-            Slot &sl = slot[t & 1];
+            Slot &sl = slot[(t - t_lo) & 1];
             const int64_t e0 = ext_lo(t), e1 = ext_hi(t), np = e1 - e0;
             // leading planes that tile t-1 also held: they wait in the carry buffer (saved below, same stream)
-            const int64_t have = t > 0 ? std::min(ext_hi(t - 1), e1) - e0 : 0;
-            const size_t hb_ = (size_t)have * plane_b, rest_b = (size_t)(np - have) * plane_b;
-            CUDA_TRY(cudaStreamWaitEvent(S.up, S.down_done[t & 1], 0));      // the slot's previous tile has left
+            const int64_t have = t > t_lo ? std::min(ext_hi(t - 1), e1) - e0 : 0;
+            // trailing planes of the range's last tile: from the edge snapshot, not from the (already rewritten) host
+            const int64_t tail = (use_edge && t == t_hi - 1) ? e1 - edge_g0 : 0;
+            const int64_t fresh = np - have - tail;             // planes read from the host state
+            const size_t hb_ = (size_t)have * plane_b, rest_b = (size_t)fresh * plane_b, tail_off = (size_t)(have + fresh) * plane_b,
+                         tail_b = (size_t)tail * plane_b;
+            CUDA_TRY(cudaStreamWaitEvent(S.up, S.down_done[(t - t_lo) & 1], 0));      // the slot's previous tile has left
             auto d2d = [&](void *dst, const void *src, size_t bytes) -> int {
                 if (bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, S.up));
                 return CYTVDN_OK;
             };
             if (int rc = d2d(sl.f, carry.f, hb_)) return rc;
-            if (int rc = dense_to_tile(sl.f, have, data, e0 + have, np - have, S.up)) return rc;
+            if (int rc = dense_to_tile(sl.f, have, data, e0 + have, np - have, S.up)) return rc;      // the input never changes
             if (!first) {
                 if (int rc = d2d(sl.r, carry.r, hb_)) return rc;
-                if (int rc = dense_to_tile(sl.r, have, recon, e0 + have, np - have, S.up)) return rc;
+                if (int rc = dense_to_tile(sl.r, have, recon, e0 + have, fresh, S.up)) return rc;
+                if (int rc = d2d((char *)sl.r + tail_off, edge.r, tail_b)) return rc;
             }
             for (int k = 0; k < nd; ++k) {
                 if (first) {
@@ -1266,15 +1303,17 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
                     if (rest_b)
                         CUDA_TRY(cudaMemcpyAsync((char *)sl.b[k] + hb_, (char *)hb[k] + (size_t)(e0 + have) * plane_b, rest_b,
                                                  cudaMemcpyHostToDevice, S.up));
+                    if (int rc = d2d((char *)sl.b[k] + tail_off, edge.b[k], tail_b)) return rc;
                     if (need_d_in) {
                         if (int rc = d2d(sl.d[k], carry.d[k], hb_)) return rc;
                         if (rest_b)
                             CUDA_TRY(cudaMemcpyAsync((char *)sl.d[k] + hb_, (char *)hd[k] + (size_t)(e0 + have) * plane_b, rest_b,
                                                      cudaMemcpyHostToDevice, S.up));
+                        if (int rc = d2d((char *)sl.d[k] + tail_off, edge.d[k], tail_b)) return rc;
                     }
                 }
             }
-            if (t + 1 < nt) {       // save what tile t+1 shares with this one before the iterations change it
+            if (t + 1 < t_hi) {     // save what tile t+1 shares with this one before the iterations change it
                 const int64_t s0 = ext_lo(t + 1) - e0, cnt = std::min(e1, ext_hi(t + 1)) - ext_lo(t + 1);
                 const size_t off = (size_t)s0 * plane_b, cb = (size_t)cnt * plane_b;
                 if (int rc = d2d(carry.f, (char *)sl.f + off, cb)) return rc;
@@ -1286,17 +1325,31 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
                     }
                 }
             }
-            CUDA_TRY(cudaEventRecord(S.up_done[t & 1], S.up));
+            CUDA_TRY(cudaEventRecord(S.up_done[(t - t_lo) & 1], S.up));
+            return CYTVDN_OK;
+        };
+        // the K planes above this device's range, as they are at the START of the pass (state m0)
+        auto snapshot_edge = [&]() -> int {
+            if (!use_edge) return CYTVDN_OK;
+            const int64_t cnt = std::min<int64_t>(n0, edge_g0 + Kp) - edge_g0;
+            if (int rc = dense_to_tile(edge.r, 0, recon, edge_g0, cnt, S.up)) return rc;
+            for (int k = 0; k < nd; ++k) {
+                CUDA_TRY(cudaMemcpyAsync(edge.b[k], (char *)hb[k] + (size_t)edge_g0 * plane_b, (size_t)cnt * plane_b,
+                                         cudaMemcpyHostToDevice, S.up));
+                if (need_d_in)
+                    CUDA_TRY(cudaMemcpyAsync(edge.d[k], (char *)hd[k] + (size_t)edge_g0 * plane_b, (size_t)cnt * plane_b,
+                                             cudaMemcpyHostToDevice, S.up));
+            }
             return CYTVDN_OK;
         };
         auto compute = [&](int t) -> int {
-            Slot &sl = slot[t & 1];
+            Slot &sl = slot[(t - t_lo) & 1];
             const int64_t e0 = ext_lo(t), e1 = ext_hi(t), np = e1 - e0;
             const int64_t c0 = (int64_t)t * core, c1 = std::min<int64_t>(n0, c0 + core);
             int64_t shape[4];
             for (int k = 0; k < nd; ++k) shape[k] = p->shape[k];
             shape[0] = np;
-            CUDA_TRY(cudaStreamWaitEvent(S.comp, S.up_done[t & 1], 0));
+            CUDA_TRY(cudaStreamWaitEvent(S.comp, S.up_done[(t - t_lo) & 1], 0));
             for (int k = 0; k < Kp; ++k) {
                 const int m = m0 + k;
                 cytvdn_step_opts o;
@@ -1309,7 +1362,7 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
                 if (e1 == n0 && e0 > 0 && p->bc_mode == 2) o.zero_wrap_mask = 1;   // plane 0 of b_0 is identically 0 under Jia-Zhao
                 const bool fi = m < nF;
                 const void *uin = (first && k == 0) ? sl.f : sl.r;      // recon = datacube.copy(), cyTVDN.py:145
-                double *sm = sums_d + ((size_t)m * nt + t) * 4;
+                double *sm = sums_d + ((size_t)m * ntl + (t - t_lo)) * 4;
                 cytvdn_step_opts oa = o;                                // A: one plane more at the upper end
                 if (e1 < n0) oa.box_hi[0] = o.box_hi[0] + 1;
                 oa.zero_wrap_mask = 0;
@@ -1320,14 +1373,14 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
                                                     sm + 1, &o, S.comp))
                     return rc;
             }
-            CUDA_TRY(cudaEventRecord(S.comp_done[t & 1], S.comp));
+            CUDA_TRY(cudaEventRecord(S.comp_done[(t - t_lo) & 1], S.comp));
             return CYTVDN_OK;
         };
         auto download = [&](int t) -> int {
-            Slot &sl = slot[t & 1];
+            Slot &sl = slot[(t - t_lo) & 1];
             const int64_t e0 = ext_lo(t);
             const int64_t c0 = (int64_t)t * core, c1 = std::min<int64_t>(n0, c0 + core);
-            CUDA_TRY(cudaStreamWaitEvent(S.down, S.comp_done[t & 1], 0));
+            CUDA_TRY(cudaStreamWaitEvent(S.down, S.comp_done[(t - t_lo) & 1], 0));
             if (int rc = tile_to_dense(recon, c0, sl.r, c0 - e0, c1 - c0, S.down)) return rc;
             if (!last)
                 for (int k = 0; k < nd; ++k) {
@@ -1337,13 +1390,22 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
                         CUDA_TRY(cudaMemcpyAsync((char *)hd[k] + (size_t)c0 * plane_b, (char *)sl.d[k] + (size_t)(c0 - e0) * plane_b,
                                                  (size_t)(c1 - c0) * plane_b, cudaMemcpyDeviceToHost, S.down));
                 }
-            CUDA_TRY(cudaEventRecord(S.down_done[t & 1], S.down));
+            CUDA_TRY(cudaEventRecord(S.down_done[(t - t_lo) & 1], S.down));
             return CYTVDN_OK;
         };
 
-        if (int rc = upload(0)) return rc;
-        for (int t = 0; t < nt; ++t) {
-            if (t + 1 < nt) if (int rc = upload(t + 1)) return rc;
+        if (ntl > 0) {
+            if (int rc = snapshot_edge()) return rc;           // first: a device with ONE tile consumes it in upload(t_lo)
+            if (int rc = upload(t_lo)) return rc;
+        }
+        if (multi && !first) {
+            // every device has read what it needs from the neighbouring ranges (the K planes below its first tile, in
+            // upload(t_lo), and the K planes above its last one) before anybody writes this pass's results back
+            CUDA_TRY(cudaStreamSynchronize(S.up));
+            if (!sh.wait()) return fail(CYTVDN_E_CUDA, "another device of the out-of-core run failed");
+        }
+        for (int t = t_lo; t < t_hi; ++t) {
+            if (t + 1 < t_hi) if (int rc = upload(t + 1)) return rc;
             if (int rc = compute(t)) return rc;
             if (int rc = download(t)) return rc;
         }
@@ -1351,24 +1413,136 @@ int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *
         // of this barrier -- was measured: no gain, the bus is busy either way.)
         CUDA_TRY(cudaStreamSynchronize(S.down));
         CUDA_TRY(cudaStreamSynchronize(S.up));
+        if (multi && !last && !sh.wait()) return fail(CYTVDN_E_CUDA, "another device of the out-of-core run failed");
     }
-    const double loop_ms = ms_since(t_loop);
-    const auto t_fin = std::chrono::steady_clock::now();
+    if (ntl > 0) {
+        std::vector<double> loc(nsums, 0.0);
+        CUDA_TRY(cudaMemcpy(loc.data(), sums_d, nsums * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < M; ++i)
+            for (int t = t_lo; t < t_hi; ++t)
+                for (int q = 0; q < 4; ++q) sh.sums_h[((size_t)i * nt + t) * 4 + q] = loc[((size_t)i * ntl + (t - t_lo)) * 4 + q];
+    }
+    return CYTVDN_OK;
+}
 
-    std::vector<double> sums_h(nsums, 0.0);
-    CUDA_TRY(cudaMemcpy(sums_h.data(), sums_d, nsums * sizeof(double), cudaMemcpyDeviceToHost));
+// host state between passes (internal, padded layout); recon's host state is the caller's array
+int stream_host_state(const cytvdn_denoise_params *p, const Dims &D, StreamShared &sh, HostPinned &hostmem)
+{
+    const int nd = p->ndim, nF = p->iters_fista;
+    const size_t elem = p->dtype == CYTVDN_F32 ? 4 : 8;
+    const int64_t full_vw = 16 / (int64_t)elem, n3p = (D.n[3] + full_vw - 1) / full_vw * full_vw;
+    const size_t plane_b = (size_t)D.n[1] * D.n[2] * n3p * elem;
+    if (sh.sp.passes > 1)
+        for (int k = 0; k < nd; ++k) {
+            if (int rc = hostmem.alloc(&sh.hb[k], (size_t)D.n[0] * plane_b)) return rc;
+            if (nF > 0 && nF > sh.sp.iters_per_pass) if (int rc = hostmem.alloc(&sh.hd[k], (size_t)D.n[0] * plane_b)) return rc;
+        }
+    sh.sums_h.assign((size_t)(p->iters_fista + p->iters_plain) * sh.sp.tiles * 4, 0.0);
+    return CYTVDN_OK;
+}
+
+void stream_finish(const cytvdn_denoise_params *p, const StreamShared &sh, double *bnorm, double *delta)
+{
+    const int M = p->iters_fista + p->iters_plain, nt = (int)sh.sp.tiles;
     for (int i = 0; i < M; ++i) {
         double s3[3] = {0.0, 0.0, 0.0};
         for (int t = 0; t < nt; ++t)                            // fixed order: deterministic
-            for (int q = 0; q < 3; ++q) s3[q] += sums_h[((size_t)i * nt + t) * 4 + q];
+            for (int q = 0; q < 3; ++q) s3[q] += sh.sums_h[((size_t)i * nt + t) * 4 + q];
         bnorm[i] = s3[0];
         delta[i] = s3[1] / s3[2];
     }
-    if (iters_done) { iters_done[0] = nF; iters_done[1] = nU; iters_done[2] = 3 | (nt << 8); }
+}
+
+int denoise_streamed(const cytvdn_denoise_params *p, const Dims &D, const void *data, void *recon, double *bnorm,
+                     double *delta, int32_t *iters_done, double *timing_ms, size_t budget)
+{
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    StreamShared sh;
+    if (int rc = make_stream_plan(p, D, budget, &sh.sp)) return rc;
+    HostPinned hostmem;
+    if (int rc = stream_host_state(p, D, sh, hostmem)) return rc;
+    const double setup_ms = ms_since(t_start);
+    const auto t_loop = std::chrono::steady_clock::now();
+    if (int rc = stream_worker(p, D, data, recon, sh, 0, (int)sh.sp.tiles, (cudaStream_t)p->stream)) return rc;
+    const double loop_ms = ms_since(t_loop);
+    const auto t_fin = std::chrono::steady_clock::now();
+    stream_finish(p, sh, bnorm, delta);
+    if (iters_done) { iters_done[0] = p->iters_fista; iters_done[1] = p->iters_plain; iters_done[2] = 3 | ((int)sh.sp.tiles << 8); }
     if (timing_ms) { timing_ms[0] = setup_ms; timing_ms[1] = loop_ms; timing_ms[2] = ms_since(t_fin); }
     return CYTVDN_OK;
 }
 }  // namespace
+
+// Sharded AND out of core (include/cytvdn_b200.h): the tiles of every pass dealt to `ndev` devices, one host thread each.
+int cytvdn_denoise_sharded_streamed(const cytvdn_denoise_params *p, int ndev, const int *devices, const void *data, void *recon,
+                                    double *bnorm, double *delta, int32_t *iters_done, double *timing_ms)
+{
+    Dims D;
+    if (int rc = validate_params(p, &D)) return rc;
+    if (!data || !recon || data == recon) return fail(CYTVDN_E_INVALID, "data / recon is NULL or aliased");
+    if (ndev < 1 || ndev > 64) return fail(CYTVDN_E_INVALID, "ndev must be in 1..64");
+    const int M = p->iters_fista + p->iters_plain;
+    if (M <= 0 || !bnorm || !delta) return fail(CYTVDN_E_INVALID, "the out-of-core schedule needs iterations and bnorm / delta");
+    if ((p->bc_mode != 2 && p->bc_mode != 3) || p->use_stopping || is_device_ptr(data) || is_device_ptr(recon))
+        return fail(CYTVDN_E_UNSUPPORTED, "the out-of-core schedule needs host arrays in and out, BC_mode 2 or 3 and no stopping test");
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    int prev_dev = 0;
+    CUDA_TRY(cudaGetDevice(&prev_dev));
+    // one geometry for all devices: the smallest budget decides (CYTVDN_STREAM_BUDGET_MB: per device, for tests)
+    size_t budget = 0;
+    { const char *env = getenv("CYTVDN_STREAM_BUDGET_MB"); if (env && atof(env) > 0) budget = (size_t)(atof(env) * 1048576.0); }
+    std::vector<int> devs(ndev);
+    for (int r = 0; r < ndev; ++r) devs[r] = devices ? devices[r] : r;
+    if (!budget) {
+        // devices that appear more than once (tests: several shards on one GPU) share that GPU's memory
+        for (int r = 0; r < ndev; ++r) {
+            CUDA_TRY(cudaSetDevice(devs[r]));
+            size_t free_b = 0, tot_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &tot_b));
+            int share = 0;
+            for (int q = 0; q < ndev; ++q) share += devs[q] == devs[r];
+            size_t b = (free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : free_b / 2) / (size_t)share;
+            if (!budget || b < budget) budget = b;
+        }
+        CUDA_TRY(cudaSetDevice(prev_dev));
+    }
+    StreamShared sh;
+    sh.ndev = ndev;
+    if (int rc = make_stream_plan(p, D, budget, &sh.sp, ndev)) return rc;
+    HostPinned hostmem;
+    if (int rc = stream_host_state(p, D, sh, hostmem)) return rc;
+    const double setup_ms = ms_since(t_start);
+    const auto t_loop = std::chrono::steady_clock::now();
+    const int nt = (int)sh.sp.tiles, per = (nt + ndev - 1) / ndev;
+    std::vector<int> rcs(ndev, CYTVDN_OK);
+    std::vector<std::string> msgs(ndev);
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r)
+        th.emplace_back([&, r] {
+            int rc = CYTVDN_OK;
+            if (cudaSetDevice(devs[r]) != cudaSuccess) rc = fail(CYTVDN_E_CUDA, "cudaSetDevice(%d) failed", devs[r]);
+            if (!rc) rc = stream_worker(p, D, data, recon, sh, std::min(nt, r * per), std::min(nt, (r + 1) * per), nullptr);
+            if (rc) { msgs[r] = g_err; sh.fail_all(); }
+            rcs[r] = rc;
+        });
+    for (auto &t : th) t.join();
+    CUDA_TRY(cudaSetDevice(prev_dev));
+    for (int r = 0; r < ndev; ++r)
+        if (rcs[r] && msgs[r].find("another device") == std::string::npos) return fail(rcs[r], "device %d: %s", devs[r], msgs[r].c_str());
+    for (int r = 0; r < ndev; ++r) if (rcs[r]) return fail(rcs[r], "device %d: %s", devs[r], msgs[r].c_str());
+    const double loop_ms = ms_since(t_loop);
+    const auto t_fin = std::chrono::steady_clock::now();
+    stream_finish(p, sh, bnorm, delta);
+    if (iters_done) { iters_done[0] = p->iters_fista; iters_done[1] = p->iters_plain; iters_done[2] = 3 | (ndev << 8); }
+    if (timing_ms) { timing_ms[0] = setup_ms; timing_ms[1] = loop_ms; timing_ms[2] = ms_since(t_fin); }
+    return CYTVDN_OK;
+}
 
 int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon, const void *reference_data,
                    double *bnorm, double *delta, double *mse, int32_t *iters_done, double *timing_ms)
@@ -1791,11 +1965,6 @@ int cytvdn_denoise(const cytvdn_denoise_params *p, const void *data, void *recon
     return CYTVDN_OK;
 }
 
-int cytvdn_denoise_sharded_streamed(const cytvdn_denoise_params *, int, const int *, const void *, void *, double *,
-                                    double *, int32_t *, double *)
-{
-    return fail(CYTVDN_E_UNSUPPORTED, "sharded out-of-core schedule: not built yet");
-}
 
 // ---- host-side plans (no GPU needed) ------------------------------------------------------------
 int cytvdn_pipeline_schedule(int nbox, int n_iter, int32_t *box, int32_t *iter, int64_t capacity, int64_t *count)
@@ -1808,6 +1977,18 @@ int cytvdn_pipeline_schedule(int nbox, int n_iter, int32_t *box, int32_t *iter, 
         if (capacity < *count) return fail(CYTVDN_E_INVALID, "capacity %lld < %lld launches", (long long)capacity, (long long)*count);
         for (size_t i = 0; i < order.size(); ++i) { box[i] = order[i].first; iter[i] = order[i].second; }
     }
+    return CYTVDN_OK;
+}
+
+int cytvdn_stream_plan_sharded(const cytvdn_denoise_params *p, int64_t budget_bytes, int ndev, int64_t *out8)
+{
+    Dims D;
+    if (int rc = validate_params(p, &D)) return rc;
+    if (!out8 || budget_bytes <= 0 || ndev < 1) return fail(CYTVDN_E_INVALID, "bad argument");
+    StreamPlan sp;
+    if (int rc = make_stream_plan(p, D, (size_t)budget_bytes, &sp, ndev)) return rc;
+    out8[0] = sp.planes_per_slot; out8[1] = sp.iters_per_pass; out8[2] = sp.core_planes; out8[3] = sp.tiles;
+    out8[4] = sp.passes; out8[5] = sp.arrays_per_slot; out8[6] = sp.plane_bytes; out8[7] = sp.host_state_bytes;
     return CYTVDN_OK;
 }
 

@@ -561,18 +561,26 @@ int cytvdn_denoise_sharded(const cytvdn_denoise_params *p, int ndev, const int *
     if (!p || !data || !recon) return fail(CYTVDN_E_INVALID, "NULL argument");
     if (ndev < 1 || ndev > 64) return fail(CYTVDN_E_INVALID, "ndev must be in 1..64");
     if (p->ndim != 4) return fail(CYTVDN_E_UNSUPPORTED, "sharding exists for 4-D datacubes only (mpi.py:252-255)");
-    if (p->isotropic_R || p->isotropic_Q) return fail(CYTVDN_E_UNSUPPORTED, "the sharded loop is anisotropic (mpi.py:317-358)");
-    if (p->bc_mode != 0 && p->bc_mode != 2 && p->bc_mode != 3)
-        return fail(CYTVDN_E_UNSUPPORTED, "sharded runs support BC_mode 2 (mpi.py:84), 0 and 3");
     const int nF = p->iters_fista, nU = p->iters_plain, nIt = nF + nU;
     if (nF < 0 || nU < 0) return fail(CYTVDN_E_INVALID, "negative iteration count");
     if (nIt > 0 && (!bnorm || !delta)) return fail(CYTVDN_E_INVALID, "bnorm / delta is NULL");
+    // out of core: the tiles run the two-pass kernels, which also know the half-isotropic pairs
     if (p->schedule == 3) return cytvdn_denoise_sharded_streamed(p, ndev, devices, data, recon, bnorm, delta, iters_done, timing_ms);
+    if (p->isotropic_R || p->isotropic_Q)
+        return fail(CYTVDN_E_UNSUPPORTED, "the in-core sharded loop is anisotropic (mpi.py:317-358); schedule 3 (out of core) "
+                                          "runs half-isotropic pairs on several devices");
+    if (p->bc_mode != 0 && p->bc_mode != 2 && p->bc_mode != 3)
+        return fail(CYTVDN_E_UNSUPPORTED, "sharded runs support BC_mode 2 (mpi.py:84), 0 and 3");
     const auto t_start = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
     const size_t elem = p->dtype == CYTVDN_F32 ? 4 : 8;
+    auto is_dev = [](const void *q) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeDevice;
+    };
     std::vector<cytvdn_shard *> sh(ndev, nullptr);
     struct Cleanup {
         std::vector<cytvdn_shard *> &v;
@@ -591,7 +599,14 @@ int cytvdn_denoise_sharded(const cytvdn_denoise_params *p, int ndev, const int *
     std::vector<std::array<unsigned char, 128>> handles(ndev);
     for (int r = 0; r < ndev; ++r) {
         sp.rank = r; sp.device = devices ? devices[r] : r;
-        if (int rc = cytvdn_shard_create(&sp, &sh[r])) return rc;
+        if (int rc = cytvdn_shard_create(&sp, &sh[r])) {
+            // the shards do not fit the devices' memory: schedule 0 falls back to the out-of-core tiles
+            if (rc == CYTVDN_E_NOMEM && p->schedule == 0 && !p->use_stopping && p->bc_mode != 0 && nIt > 0 && !is_dev(data) && !is_dev(recon)) {
+                for (auto &q : sh) { cytvdn_shard_destroy(q); q = nullptr; }
+                return cytvdn_denoise_sharded_streamed(p, ndev, devices, data, recon, bnorm, delta, iters_done, timing_ms);
+            }
+            return rc;
+        }
         if (int rc = cytvdn_shard_export(sh[r], handles[r].data())) return rc;
     }
     for (int r = 0; r < ndev; ++r) {

@@ -78,12 +78,15 @@ tv_fused_kernel(const FusedParams<T> P)
     const int lane = threadIdx.x & 31;
     // All reads keep the default L2 policy: marking the last-use ("self") loads evict-first was measured
     // 25 % slower -- inside a wave a neighbour may still need the line.
-    auto ld_self = [&](const T *p) -> Vec<T, VW> { return ld_ro<T, VW>(p); };
+    // (per-warp ordering: coherent loads -- ptxas sinks read-only loads below the cheap per-warp barrier, next to the
+    //  neighbour loads, where they would be fetched concurrently with them)
+    constexpr bool WO = WarpOrder<T>::value;
+    auto ld_self = [&](const T *p) -> Vec<T, VW> { return WO ? ld_ro_ordered<T, VW>(p) : ld_ro<T, VW>(p); };
     double acc[SSE ? 4 : 3] = {};
     constexpr int NFAR = AX2 ? 3 : 2;                 // far axes 0, 1 (, 2)
 
     TileSched sched{P.W.ticket + 1, S.dynamic, 0};
-    for (int32_t t = sched.first(); t < S.ntiles; t = sched.template advance<true>(t)) {
+    for (int32_t t = sched.first(); t < S.ntiles; t = sched.template advance<!WO>(t)) {
         sched.prefetch();
         // Inactive threads (tail of a slab) run on valid addresses of the slab start and only skip the
         // stores and the sums: no divergence before the loads, so all of them are issued back to back.
@@ -137,7 +140,8 @@ const bool lo_peer = PEER && c.i == 0 && P.lo_u != nullptr;
         // reads x2) -- neither L1 nor L2 merges a miss into a fill that is still in flight.
         // The barrier carries a predicate computed from the shuffle result, so it cannot be scheduled
         // before the shuffle, i.e. before this warp's own lines have arrived.
-        if (__syncthreads_or(left != left) == 0x5a5a5a5a) return;       // never taken (result is 0 or 1)
+        if (WO) { if (order_after(left) == 0x5a5a5a5au) return; }        // never taken (result is 0 or 1)
+        else if (__syncthreads_or(left != left) == 0x5a5a5a5a) return;
 #pragma unroll
         for (int d = 0; d < NFAR; ++d) {
             pv[d] = ld_ro_ordered<T, VW>(d == 0 ? pv0_ptr : P.uin + poff[d]);
@@ -273,8 +277,10 @@ tv_fused_iso_kernel(const FusedParams<T> P)
     const T rclipR = clip_rcp(P.clip[0]), rclipQ = clip_rcp(P.clip[2]);
     auto fista = [&](T v, T d) -> T { return FISTA ? (v + P.tk * (v - d)) : v; };
 
+    constexpr bool WO = WarpOrder<T>::value;
+    auto ld_self = [&](const T *p) -> Vec<T, VW> { return WO ? ld_ro_ordered<T, VW>(p) : ld_ro<T, VW>(p); };
     TileSched sched{P.W.ticket + 1, S.dynamic, 0};
-    for (int32_t t = sched.first(); t < S.ntiles; t = sched.template advance<true>(t)) {
+    for (int32_t t = sched.first(); t < S.ntiles; t = sched.template advance<!WO>(t)) {
         sched.prefetch();
         const Coord c = locate<VW>(S, t);
         const int64_t e = c.e;
@@ -293,20 +299,21 @@ tv_fused_iso_kernel(const FusedParams<T> P)
         }
 
         // ---------------- phase 1: own voxels ------------------------------------------------------------
-        const Vec<T, VW> us = ld_ro<T, VW>(P.uin + e);
-        const Vec<T, VW> f = ld_ro<T, VW>(P.f + e);
-        const Vec<T, VW> b3 = ld_ro<T, VW>(P.bin[3] + e);
+        const Vec<T, VW> us = ld_self(P.uin + e);
+        const Vec<T, VW> f = ld_self(P.f + e);
+        const Vec<T, VW> b3 = ld_self(P.bin[3] + e);
         Vec<T, VW> d3;
-        if (FISTA) d3 = ld_ro<T, VW>(P.din[3] + e);
+        if (FISTA) d3 = ld_self(P.din[3] + e);
         Vec<T, VW> bs[3], ds[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            bs[d] = ld_ro<T, VW>(P.bin[d] + e);
-            if (FISTA) ds[d] = ld_ro<T, VW>(P.din[d] + e);
+            bs[d] = ld_self(P.bin[d] + e);
+            if (FISTA) ds[d] = ld_self(P.din[d] + e);
         }
         T left = __shfl_up_sync(0xffffffffu, us.v[VW - 1], 1);
         // ---------------- phase 2: neighbours, one memory latency later (see tv_fused_kernel) -------------
-        if (__syncthreads_or(left != left) == 0x5a5a5a5a) return;       // never taken
+        if (WO) { if (order_after(left) == 0x5a5a5a5au) return; }        // never taken
+        else if (__syncthreads_or(left != left) == 0x5a5a5a5a) return;
         Vec<T, VW> pv[3], uy[3], by[3], dy[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {

@@ -47,6 +47,26 @@ int main(void)
     for (size_t x = 0; x < n; ++x) change = fmax(change, fabs((double)recon[x] - data[x]));
     printf("%d FISTA iterations (schedule %d), loop %.3f ms, delta[0]=%.3e delta[last]=%.3e, max |recon-data| = %.2f\n",
            done[0], done[2] & 0xff, ms[1], delta[0], delta[ITERS - 1], change);
+
+    /* The same run sharded over scan axis 0 from this one process (what cyTVDN/mpi.py does with one MPI rank per
+       tile): every device -- two GPUs when the machine has them, else the same GPU twice -- takes a tile with one
+       overlap plane, the halo planes are pushed by the copy engines under the interior sweep.  The result must equal
+       the single-GPU one bit for bit. */
+    {
+        float *recon2 = malloc(n * sizeof *recon2);
+        double bnorm2[ITERS], delta2[ITERS];
+        const int devices[2] = {0, ndev > 1 ? 1 : 0};
+        if (cytvdn_denoise_sharded(&p, 2, devices, data, recon2, bnorm2, delta2, done, ms) != CYTVDN_OK) {
+            fprintf(stderr, "cytvdn_denoise_sharded failed: %s\n", cytvdn_last_error());
+            return 1;
+        }
+        size_t diff = 0;
+        for (size_t x = 0; x < n; ++x) diff += recon2[x] != recon[x];
+        printf("sharded over devices {%d, %d}: %d iterations on %d shards, %zu voxels differ from the single-GPU result, "
+               "delta[last]=%.3e\n", devices[0], devices[1], done[0], done[2] >> 8, diff, delta2[ITERS - 1]);
+        free(recon2);
+        if (diff) return 3;
+    }
     free(data); free(recon);
     return delta[ITERS - 1] < delta[0] ? 0 : 2;
 }

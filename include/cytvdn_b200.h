@@ -284,6 +284,11 @@ int cytvdn_last_trace(double *ms, const char **what, int capacity, int *count);
 int cytvdn_pipeline_schedule(int nbox, int n_iter, int32_t *box, int32_t *iter, int64_t capacity,
                              int64_t *count);
 int cytvdn_stream_plan(const cytvdn_denoise_params *params, int64_t budget_bytes, int64_t *out8);
+/* the same for cytvdn_denoise_sharded_streamed: budget per device (two slots + carry + the K-plane edge snapshot =
+   2.75 P planes of every array), tiles a multiple of `ndev` of equal size; device r takes tiles
+   [r * ceil(tiles / ndev), (r + 1) * ceil(tiles / ndev)) of every pass.  Per pass: every device copies in its first tile
+   and the K planes above its last tile, BARRIER, then streams its tiles, BARRIER. */
+int cytvdn_stream_plan_sharded(const cytvdn_denoise_params *params, int64_t budget_bytes_per_device, int ndev, int64_t *out8);
 
 /*
  * ---------------------------------------------------------------------------------------------------------------

@@ -855,14 +855,24 @@ def test_pcie_pipeline_equals_unpipelined(tv, shape, dt, iters, fista, boxes, pi
     assert np.array_equal(got[0], ref[0])
     np.testing.assert_allclose(got[1].astype(np.float64), ref[1].astype(np.float64), rtol=1e-6)
     np.testing.assert_allclose(got[2].astype(np.float64), ref[2].astype(np.float64), rtol=1e-6)
-    # cases the pipeline must decline: periodic boundary, stopping test, reference_data, device arrays
+    # cases the pipeline must decline: periodic boundary, stopping test, device arrays
     t2 = {}
     fn(data, mu, 5, FISTA=fista, BC_mode=0, quiet=True, schedule="fused", timing=t2)
     assert t2["pipeline_boxes"] == 0
     fn(data, mu, 5, FISTA=fista, stopping_relative_change=1e-9, quiet=True, schedule="fused", timing=t2)
     assert t2["pipeline_boxes"] == 0
-    fn(data, mu, 5, FISTA=fista, reference_data=np.asarray(data), quiet=True, schedule="fused", timing=t2)
+    # reference_data no longer switches the pipeline off (round 2: sum (ref - recon)^2 rides along in the fused pass,
+    # box by box): same reconstruction and the same MSE series as the unpipelined run
+    ref_data = (np.asarray(data) * 0.97).astype(dt)
+    r_pipe = fn(data, mu, 7, FISTA=fista, reference_data=ref_data, quiet=True, schedule="fused", timing=t2)
+    assert t2["pipeline_boxes"] == min(boxes, shape[0] // 2)
+    monkeypatch.setenv("CYTVDN_PIPELINE", "0")
+    r_flat = fn(data, mu, 7, FISTA=fista, reference_data=ref_data, quiet=True, schedule="fused", timing=t2)
     assert t2["pipeline_boxes"] == 0
+    assert np.array_equal(r_pipe[0], r_flat[0]) and len(r_pipe) == 4
+    np.testing.assert_allclose(r_pipe[3].astype(np.float64), r_flat[3].astype(np.float64), rtol=1e-6)
+    want0 = float(((np.asarray(data).astype(np.float64) - ref_data.astype(np.float64)) ** 2).sum())
+    assert abs(float(r_pipe[3][0]) - want0) <= 1e-4 * want0
 
 
 def test_pcie_pipeline_default_threshold(tv):

@@ -167,3 +167,107 @@ def test_stream_plan_errors():
     assert rc == 3 and b"do not fit" in _lib.load().cytvdn_last_error()
     rc, _ = stream_plan((41, 5, 6, 16), "float32", 0, 0, 1 << 30)
     assert rc == 1
+
+
+@pytest.mark.parametrize("shape,nF,nU,planes,ndev", [
+    ((41, 5, 6, 16), 23, 0, 12, 2), ((41, 5, 6, 16), 7, 6, 12, 3), ((64, 2, 3, 8), 9, 0, 16, 4), ((30, 4, 5, 13), 0, 9, 8, 2),
+    ((9, 4, 6, 8), 7, 0, 8, 4), ((100, 2, 3, 8), 40, 0, 24, 3),
+])
+@pytest.mark.parametrize("order", ["forward", "reverse", "last_first"])
+def test_sharded_stream_plan_replay(shape, nF, nU, planes, ndev, order):
+    """Replay `cytvdn_denoise_sharded_streamed`'s schedule for several devices on version numbers, with the devices'
+    tile loops interleaved adversarially between the two barriers of a pass: whatever the order, every plane a tile
+    copies in -- from the shared host state, the carry buffer or the edge snapshot -- holds the iterate of the pass's
+    start, and every plane ends at the final iterate."""
+    lib = _lib.load()
+    nd, n0, M = len(shape), shape[0], nF + nU
+    n3p = -(-shape[-1] // 4) * 4
+    plane_b = int(np.prod(shape[1:-1])) * n3p * 4
+    arrays = 2 + nd * (2 if nF else 1)
+    budget = (11 * arrays * plane_b // 4) * planes + 1000
+    P_ = _lib.DenoiseParams()
+    P_.ndim, P_.dtype = nd, 0
+    for k, n in enumerate(shape):
+        P_.shape[k] = n
+    P_.iters_fista, P_.iters_plain, P_.bc_mode = nF, nU, 2
+    out = (C.c_int64 * 8)()
+    assert lib.cytvdn_stream_plan_sharded(C.byref(P_), int(budget), ndev, out) == 0
+    P, K, core, nt, passes = out[0], out[1], out[2], out[3], out[4]
+    assert P == planes and K == min(M, max(1, P // 4)) and core <= P - 2 * K and nt == -(-n0 // core)
+    per = -(-nt // ndev)
+    ranges = [(min(nt, r * per), min(nt, (r + 1) * per)) for r in range(ndev)]
+    assert sum(hi - lo for lo, hi in ranges) == nt
+    host = [0] * n0
+    m0 = 0
+    while m0 < M:
+        Kp = min(K, M - m0)
+        first = m0 == 0
+        tiles = [(max(0, t * core - Kp), min(n0, min(n0, (t + 1) * core) + Kp), t * core, min(n0, (t + 1) * core)) for t in range(nt)]
+        assert all(e1 - e0 <= P for e0, e1, _, _ in tiles)
+
+        class Dev:
+            def __init__(self, lo, hi):
+                self.lo, self.hi, self.loaded, self.carry, self.edge = lo, hi, {}, {}, {}
+
+            def read_host(self, g_):
+                # pass 0 builds its state from the (never written) input; later passes read the shared host state
+                if not first:
+                    assert host[g_] == m0, f"plane {g_} read from the host at iterate {host[g_]}, pass starts at {m0}"
+                return m0
+
+            def upload(self, t):
+                e0, e1, _, _ = tiles[t]
+                have = min(tiles[t - 1][1], e1) - e0 if t > self.lo else 0
+                edge_g0 = min(n0, self.hi * core)
+                tail = (e1 - edge_g0) if (t == self.hi - 1 and self.hi < nt and not first) else 0
+                st = {g_: self.carry[g_] for g_ in range(e0, e0 + have)}
+                for g_ in range(e0 + have, e1 - tail):
+                    st[g_] = self.read_host(g_)
+                for g_ in range(e1 - tail, e1):
+                    st[g_] = self.edge[g_]
+                assert all(v == m0 for v in st.values())
+                self.loaded[t] = st
+                self.carry = {}
+                if t + 1 < self.hi:
+                    for g_ in range(tiles[t + 1][0], min(e1, tiles[t + 1][1])):
+                        self.carry[g_] = st[g_]
+
+            def snapshot(self):
+                if self.hi < nt and self.hi > self.lo and not first:
+                    g0 = min(n0, self.hi * core)
+                    self.edge = {g_: self.read_host(g_) for g_ in range(g0, min(n0, g0 + Kp))}
+
+            def run_tile(self, t):
+                e0, e1, c0, c1 = tiles[t]
+                if t + 1 < self.hi:
+                    self.upload(t + 1)
+                st = self.loaded.pop(t)
+                for k in range(Kp):
+                    lo = e0 + (k + 1 if e0 > 0 else 0)
+                    hi = e1 - (k + 1 if e1 < n0 else 0)
+                    new = dict(st)
+                    for g_ in range(lo, hi):
+                        for nb in (g_ - 1, g_, g_ + 1):
+                            if 0 <= nb < n0:
+                                assert st[nb] == m0 + k
+                        new[g_] = m0 + k + 1
+                    st = new
+                for g_ in range(c0, c1):
+                    assert st[g_] == m0 + Kp
+                    host[g_] = m0 + Kp                      # written back to the shared host state
+
+        devs = [Dev(lo, hi) for lo, hi in ranges]
+        for d in devs:                                      # phase 1 (before the barrier): first tile + edge snapshot
+            if d.hi > d.lo:
+                d.snapshot()                                # (same copy stream, this order: one-tile devices use it at once)
+                d.upload(d.lo)
+        seq = list(range(ndev))                             # phase 2: tile loops in an adversarial device order
+        if order == "reverse":
+            seq = seq[::-1]
+        elif order == "last_first":
+            seq = seq[-1:] + seq[:-1]
+        for r in seq:                                       # one device runs its whole pass before the next one starts
+            for t in range(devs[r].lo, devs[r].hi):
+                devs[r].run_tile(t)
+        m0 += Kp
+    assert host == [M] * n0

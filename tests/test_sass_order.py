@@ -1,7 +1,7 @@
 """Pins the load ordering the fused and half-step-B kernels depend on (fused.cuh) in the SHIPPED
-binary: the self loads (``LDG.E.128.CONSTANT``) are issued first, the lane shuffle consumes one of them, a
-predicate-carrying barrier (``BAR.RED.OR``) follows, and only behind it come the neighbour loads (plain coherent
-``LDG.E.128``).  Issued together with the self loads, every neighbour line would be fetched from HBM a second time
+binary: the self loads (``LDG.E.128``) are issued first, the lane shuffle consumes one of them, a
+predicate-carrying barrier (``BAR.RED.OR``; float kernels: a named barrier that only the warp's own 32 threads join)
+follows, and only behind it come the neighbour loads.  Issued together with the self loads, every neighbour line would be fetched from HBM a second time
 (neither L1 nor L2 merges a miss into a fill in flight): DRAM reads x2, the fused pass slower than two passes.  Round 1
 guarded this only with a relative timing test on the GPU; a future ptxas that hoists the loads now fails here, on CPU.
 
@@ -39,7 +39,7 @@ VEC_LD = re.compile(r"(@!?U?P\d+\s+)?LDG\.E(\.EF)?\.128(\.CONSTANT)?\s")       #
 VEC_ST = re.compile(r"(@!?U?P\d+\s+)?STG\.E(\.EF)?\.128\s")                           # .STRONG.GPU loads of the reduction)
 
 
-def check_two_phase(ins, n_self, n_nbr, strict=True):
+def check_two_phase(ins, n_self, n_nbr, strict=True, warp_barrier=True):
     red = [k for k, (_, i) in enumerate(ins) if i.startswith("BAR.RED")]
     assert len(red) == 1, f"expected one predicate barrier in the sweep loop, found {len(red)}"
     bar = red[0]
@@ -54,8 +54,13 @@ def check_two_phase(ins, n_self, n_nbr, strict=True):
         assert len(before) == n_self, f"{len(before)} self loads in front of the barrier, expected {n_self}"
         assert len(between) == n_nbr, (f"{len(between)} neighbour loads between the barrier and the first store, expected "
                                        f"{n_nbr}: a hoisted neighbour load is fetched from HBM twice")
-        # the read-only (.CONSTANT) path is used for self loads only: ptxas may hoist those over bar.sync
-        assert all(k < bar for k in loads if ".CONSTANT" in ins[k][1])
+        if warp_barrier:
+            # fused float kernels (round 2): the per-warp named barrier (32 threads), all loads on the coherent path
+            assert "0x20" in ins[bar][1], ins[bar][1]
+            assert not any(".CONSTANT" in ins[k][1] for k in loads)
+        else:
+            # CTA-wide barrier: the read-only (.CONSTANT) path is used for self loads only (ptxas may move those)
+            assert all(k < bar for k in loads if ".CONSTANT" in ins[k][1])
     else:
         # register-starved instantiations (float64): ptxas sinks a few SELF loads below the barrier, which is harmless;
         # what must hold is that every neighbour load (coherent path) is behind it
@@ -81,4 +86,4 @@ def test_fused_variants_keep_the_order():
 
 
 def test_half_step_b_keeps_the_order():
-    check_two_phase(sass_of("tv_datacube_kernelIfLi4ELb1ELb0E"), 6, 3)     # f, u, b x4 | b+ on the three far axes
+    check_two_phase(sass_of("tv_datacube_kernelIfLi4ELb1ELb0E"), 6, 3, warp_barrier=False)     # f, u, b x4 | b+ on the three far axes

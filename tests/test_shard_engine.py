@@ -91,3 +91,38 @@ def test_engine_partition_matches_shardplan():
                     assert p.valid[0] == (lo, hi) and p.has_lo[0] == has_lo and p.has_hi[0] == has_hi
                     assert p.local_shape[0] == (hi - lo) + has_lo + has_hi
                     assert p.own_lo[0] == int(has_lo) and p.own_hi[0] == p.local_shape[0] - int(has_hi)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dt,iters,fista,kw,ndev,planes", [
+    ((40, 6, 8, 12), "float32", [9, 5], True, {}, 3, 12),            # several tiles per device, FISTA -> plain inside a pass
+    ((37, 5, 6, 13), "float32", 11, True, {}, 2, 10),                # odd rows (padded), uneven tile sizes
+    ((30, 4, 6, 8), "float64", 8, False, {}, 2, 8),                  # unaccelerated, float64
+    ((33, 4, 6, 8), "float32", 10, True, {"isotropic_R": True, "isotropic_Q": True}, 3, 9),
+    ((26, 4, 6, 8), "float32", 9, True, {"BC_mode": 3}, 2, 8),       # clamped mirror
+    ((9, 4, 6, 8), "float32", 7, True, {}, 4, 8),                    # fewer tiles than devices
+    ((24, 4, 6, 8), "float32", 30, True, {}, 1, 8),                  # one device through the sharded entry
+])
+def test_sharded_out_of_core_equals_in_core(shape, dt, iters, fista, kw, ndev, planes, monkeypatch):
+    """`cytvdn_denoise_sharded_streamed` (config 5 on fewer GPUs than its state fits: README.md:104-120 of the
+    reference): the out-of-core tiles of every pass dealt to several devices -- here all of them cuda:0, one host thread
+    each -- with the K halo planes a device needs from the neighbouring range snapshotted before anybody writes back.
+    Reconstruction bit-identical to the in-core single-GPU run; bnorm / delta to 1e-6."""
+    import cytvdn_b200 as tv
+    rng = np.random.default_rng(sum(shape))
+    data = rng.poisson(rng.uniform(20, 500, shape)).astype(dt)
+    mu = np.array([1, 1, .5, .5], dtype=dt)
+    ref = tv.denoise4D(data, mu, iters, fista, quiet=True, schedule="two_pass", **kw)
+    elem = 4 if dt == "float32" else 8
+    n3p = -(-shape[3] // (16 // elem)) * (16 // elem)
+    plane = shape[1] * shape[2] * n3p * elem
+    arrays = 2 + 4 * (2 if fista else 1)
+    # per-device budget that gives `planes` planes per slot (2.75 slots-worth for several devices, 2.5 for one)
+    budget = (2.75 if ndev > 1 else 2.5) * arrays * plane * planes + 4096
+    monkeypatch.setenv("CYTVDN_STREAM_BUDGET_MB", repr(budget / 1048576.0))
+    tm = {}
+    got = tv.denoise4D(data, mu, iters, fista, quiet=True, schedule="streamed", devices=[0] * ndev, timing=tm, **kw)
+    assert tm["schedule"] == "streamed" and tm["devices"] == ndev
+    assert np.array_equal(got[0], ref[0]), float(np.abs(got[0] - ref[0]).max())
+    np.testing.assert_allclose(got[1].astype(np.float64), ref[1].astype(np.float64), rtol=1e-5)
+    np.testing.assert_allclose(got[2].astype(np.float64), ref[2].astype(np.float64), rtol=1e-5)

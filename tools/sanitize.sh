@@ -7,4 +7,5 @@ timeout 300 python tools/sanitizer_cases.py > gpurun_out/r2_sanitizer_plain.log 
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitizer_cases.py > gpurun_out/r2_sanitizer_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer cases ok|Error|hazard" gpurun_out/r2_sanitizer_$tool.log | head -12
+  tail -4 gpurun_out/r2_sanitizer_$tool.log | cut -c1-300
 done

@@ -39,7 +39,9 @@ def main():
             for pad in ("1", "0"):
                 os.environ["CYTVDN_PAD_ROWS"] = pad
                 a = tv.denoise4D(x, mu4(dt), [4, 3], True, quiet=True, schedule="two_pass", **kw)
-                b = tv.denoise4D(x, mu4(dt), [4, 3], True, quiet=True, schedule=None if kw.get("BC_mode") == 3 else "fused", **kw)
+                vec = pad == "1" or shape[3] % (4 if dt == "float32" else 2) == 0
+                auto = kw.get("BC_mode") == 3 or (kw.get("isotropic_R") and not vec)     # variants that need aligned rows
+                b = tv.denoise4D(x, mu4(dt), [4, 3], True, quiet=True, schedule=None if auto else "fused", **kw)
                 assert np.array_equal(a[0], b[0]), (shape, dt, kw, pad)
                 n += 2
         os.environ["CYTVDN_PAD_ROWS"] = "1"
