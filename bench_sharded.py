@@ -43,10 +43,16 @@ def make_engine(sharded, gshape, world, rank, mu, max_iters, local):
 
 
 def close_engine(eng):
+    eng.close_collective()                                    # synchronise, barrier, unmap neighbours, barrier, free
+
+
+def all_ok(flag, dev):
+    """True iff `flag` is true on EVERY rank (a rank-local failure must never leave the others inside a collective)."""
+    import torch
     import torch.distributed as dist
-    eng.synchronize()
-    dist.barrier()                                            # nobody frees an arena a neighbour still pushes into
-    eng.close()
+    t = torch.tensor([int(bool(flag))], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
 
 
 def parity_check(dev, rank, world, mu):
@@ -90,7 +96,9 @@ def run_sharded(args):
     os.environ.setdefault("MASTER_PORT", "29511")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    # a rank that dies must not keep the others waiting for NCCL's default 10 minutes
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=150))
     rc = 0
     try:
         per = tuple(args.shape) if args.shape else SHARD_PER_GPU
@@ -129,22 +137,26 @@ def run_sharded(args):
             close_engine(eng)
             eng = None
             torch.cuda.empty_cache()
-            x = synth.stem4d_device(gshape, offset0=plan.read[0][0], lshape0=n0, seed=2, counts=500.0, device=dev)
-            got = sharded.denoise4D_sharded(x, mu, 4, True, plan=plan, schedule="two_pass", engine=False)[0]
-            other = _checksum(got[plan.owned_local[0]])
-            del got, x
-            torch.cuda.empty_cache()
-            same = torch.tensor([int(mine == other)], device=dev)
-            dist.all_reduce(same, op=dist.ReduceOp.MIN)
-            tot = torch.tensor([mine >> 8], dtype=torch.int64, device=dev)         # >> 8: the sum over ranks stays in int64
-            dist.all_reduce(tot)
-            check["fullsize_engine_vs_nccl_two_pass"] = {"iterations": 4, "identical_on_all_ranks": bool(same.item()),
-                                                         "recon_checksum": int(tot.item())}
-            if not bool(same.item()):
-                if rank == 0:
-                    print(json.dumps({"error": "full-size engine vs two-pass checksum mismatch", "check": check}),
-                          file=sys.stderr, flush=True)
-                return 3
+            need = 10 * int(np.prod(plan.local_shape)) * 4 + (3 << 30)           # x + 9 state arrays + slack
+            if all_ok(torch.cuda.mem_get_info(dev)[0] > need, dev):
+                x = synth.stem4d_device(gshape, offset0=plan.read[0][0], lshape0=n0, seed=2, counts=500.0, device=dev)
+                got = sharded.denoise4D_sharded(x, mu, 4, True, plan=plan, schedule="two_pass", engine=False)[0]
+                other = _checksum(got[plan.owned_local[0]])
+                del got, x
+                torch.cuda.empty_cache()
+                same = all_ok(mine == other, dev)
+                tot = torch.tensor([mine >> 8], dtype=torch.int64, device=dev)     # >> 8: the sum over ranks stays in int64
+                dist.all_reduce(tot)
+                check["fullsize_engine_vs_nccl_two_pass"] = {"iterations": 4, "identical_on_all_ranks": same,
+                                                             "recon_checksum": int(tot.item())}
+                if not same:
+                    if rank == 0:
+                        print(json.dumps({"error": "full-size engine vs two-pass checksum mismatch", "check": check}),
+                              file=sys.stderr, flush=True)
+                    return 3
+            else:
+                check["fullsize_engine_vs_nccl_two_pass"] = {"skipped": "not enough free device memory on some rank",
+                                                             "free_gb_rank0": torch.cuda.mem_get_info(dev)[0] / 1e9}
         if use_engine:
             eng = make_engine(sharded, gshape, world, rank, mu, max_it, local)
         else:
@@ -267,8 +279,14 @@ def run_sharded(args):
             try:
                 iters = args.e2e_iters
                 if use_engine:
-                    host_in = tv.pinned_empty(eng.local_shape, np.float32)
-                    host_out = tv.pinned_empty(eng.owned_shape, np.float32)
+                    host_in = host_out = None
+                    try:                                      # page-locked host memory may run out on one rank only
+                        host_in = tv.pinned_empty(eng.local_shape, np.float32)
+                        host_out = tv.pinned_empty(eng.owned_shape, np.float32)
+                    except Exception:
+                        pass
+                    if not all_ok(host_out is not None, dev):
+                        raise MemoryError("page-locked host buffers for the end-to-end run could not be allocated on every rank")
                     torch.from_numpy(host_in).copy_(eng.array("orig"))
                     torch.cuda.synchronize()
                     call = lambda n: sharded.denoise4D_engine(host_in, mu, n, True, gshape=gshape, out=host_out, engine=eng)
@@ -368,8 +386,16 @@ def run_sharded(args):
                         eng = None
                     torch.cuda.empty_cache()
                     plan5 = sharded.ShardPlan(full, world, rank)
-                    x5 = synth.stem4d_device(full, offset0=plan5.read[0][0], lshape0=plan5.local_shape[0], seed=2, counts=500.0, device=dev)
-                    sh5 = sharded.CudaShard(plan5, x5, mu, None, fista=True, n_iter=args.warmup + args.steps, fused=False)
+                    x5 = sh5 = None
+                    try:                                      # allocation may fail on one rank only: decide together
+                        x5 = synth.stem4d_device(full, offset0=plan5.read[0][0], lshape0=plan5.local_shape[0], seed=2, counts=500.0, device=dev)
+                        sh5 = sharded.CudaShard(plan5, x5, mu, None, fista=True, n_iter=args.warmup + args.steps, fused=False)
+                    except Exception as ex:
+                        alloc_err = repr(ex)[:200]
+                    if not all_ok(sh5 is not None, dev):
+                        del sh5, x5
+                        torch.cuda.empty_cache()
+                        raise MemoryError("the in-place two-pass state (10 arrays, 173 GB per GPU) did not fit on every rank")
                     tk5, it5 = 1.0, 0
                     for k in range(args.warmup + args.steps):
                         if k == args.warmup:
@@ -418,13 +444,15 @@ def run_sharded(args):
                     "clocks": clk, "check": check, "single_gpu_same_shard": alone, "timeline": timeline,
                     "strong_scaling_config5": strong}
             print(json.dumps(line), flush=True)
-    finally:
-        try:
-            if 'eng' in locals() and eng is not None:
-                close_engine(eng)
-        except Exception:
-            pass
-        dist.destroy_process_group()
+    except BaseException:
+        # a failing rank leaves at once (no collective tear-down the others might not join); torchrun then stops the rest
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+    if 'eng' in locals() and eng is not None:
+        close_engine(eng)
+    dist.destroy_process_group()
     return rc
 
 

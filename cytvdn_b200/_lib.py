@@ -105,6 +105,7 @@ PROTOTYPES = {
     "cytvdn_last_trace": (C.c_int, [_dp, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_int)]),
     "cytvdn_shard_create": (C.c_int, [C.POINTER(ShardParams), _vpp]),
     "cytvdn_shard_destroy": (C.c_int, [_vp]),
+    "cytvdn_shard_disconnect": (C.c_int, [_vp]),
     "cytvdn_shard_info": (C.c_int, [_vp, _i64p]),
     "cytvdn_shard_export": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
     "cytvdn_shard_connect": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_ubyte)]),

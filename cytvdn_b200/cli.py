@@ -10,11 +10,12 @@ lambda itself (no ``mu/32`` default, `mpi.py:249-250`), the data are processed a
 ``BC_mode`` is 2 (`mpi.py:84`), every rank reads only its own block (owned planes + one overlap plane per
 neighbour, `mpi.py:165-180`) and writes only its owned block (`mpi.py:470-498`).
 
-File formats: ``.npy`` (memory-mapped, any size) in and out.  On one GPU the arrays stay on the host: the library
+File formats: ``.npy`` (memory-mapped, any size) in and out; ``-o x.emd`` / ``.h5`` writes the reference's EMD v0.7
+layout (`mpi.py:440-498`) when h5py is importable.  On one GPU the arrays stay on the host: the library
 overlaps the PCIe copies with the iterations and switches to its out-of-core schedule (``--schedule streamed`` forces
 it) when the state does not fit in the GPU's memory.  ``.h5`` / ``.emd`` input is read through h5py when
-that package is importable (dataset path ``-p``); the reference's ``.dm3/.dm4`` readers (py4DSTEM / ncempy) and
-its EMD v0.7 writer are out of scope.  Unlike the reference, FISTA (`mpi.py:310-311` "haven't done FISTA yet"),
+that package is importable (dataset path ``-p``); the reference's ``.dm3/.dm4`` readers (py4DSTEM / ncempy) are out
+of scope.  Unlike the reference, FISTA (`mpi.py:310-311` "haven't done FISTA yet"),
 hybrid iteration counts and 3-D input (single GPU only) work, and ``--stop`` enables the relative-change stopping
 criterion that its to-do list mentions (`README.md:34`).
 """
@@ -41,7 +42,7 @@ def _str2bool(v):
 def build_parser():
     p = argparse.ArgumentParser(prog="cytvdn_b200.cli", description="Launch TV denoising on B200 GPUs (cyTVMPI flags).")
     p.add_argument("-i", "--input", type=os.path.abspath, nargs=1, required=True, help="input file (.npy, .h5/.emd)")
-    p.add_argument("-o", "--output", type=os.path.abspath, nargs=1, required=True, help="output file (.npy)")
+    p.add_argument("-o", "--output", type=os.path.abspath, nargs=1, required=True, help="output file (.npy, or .emd/.h5 with h5py)")
     p.add_argument("-d", "--dimensions", type=int, nargs=1, required=True, help="Number of Dimensions (3 or 4)")
     p.add_argument("-f", "--fista", type=_str2bool, nargs=1, default=[False], help="Use acceleration? 0 or 1.")
     p.add_argument("-n", "--niterations", type=int, nargs="+", required=True,
@@ -86,11 +87,57 @@ def read_block(data, slices):
     return np.array(data[slices], dtype=np.float32, order="C")       # always a private, writable copy
 
 
+def is_hdf5(path):
+    return os.path.splitext(path)[1].lower() in (".h5", ".hdf5", ".emd")
+
+
+def create_emd(path, shape):
+    """An empty EMD v0.7 file with the group layout the reference hard-codes (`mpi.py:440-490`): top-level group
+    ``4DSTEM_experiment`` (emd_group_type 2, version 0.7), the (empty) data groups, ``data/datacubes/datacube_0``
+    with the float32 dataset ``data`` and the four uncalibrated dimension vectors ``dim1..dim4``.  Needs h5py
+    (optional dependency; the reference needs the parallel ``mpio`` build, here the ranks write one after the other)."""
+    try:
+        import h5py
+    except ImportError as e:
+        raise SystemExit(f"{path}: HDF5 / EMD output needs h5py, which is not installed ({e}); write .npy instead")
+    with h5py.File(path, "w") as f:
+        top = f.create_group("4DSTEM_experiment")
+        top.attrs.create("emd_group_type", 2)
+        top.attrs.create("version_major", 0)
+        top.attrs.create("version_minor", 7)
+        top.create_group("metadata")
+        data = top.create_group("data")
+        cubes = data.create_group("datacubes")
+        for name in ("counted_datacubes", "diffractionslices", "realslices", "pointlists", "pointlistarrays"):
+            data.create_group(name)
+        dc = cubes.create_group("datacube_0")
+        dc.create_dataset("data", tuple(shape), dtype="float32")
+        dc.attrs.create("emd_group_type", 1)
+        dc.attrs.create("metadata", -1)
+        for k, (n, label) in enumerate(zip(shape, ("R_x", "R_y", "Q_x", "Q_y")), start=1):
+            d = dc.create_dataset(f"dim{k}", (n,))
+            d[...] = np.arange(0, n)
+            d.attrs.create("name", np.bytes_(label))
+            d.attrs.create("units", np.bytes_("[pix]"))
+
+
 def create_output(path, shape):
+    """The output file: a memory-mapped .npy (returned, so that a single process can write straight into it) or an
+    EMD v0.7 HDF5 file (returns None: written block by block with ``write_block``)."""
+    if is_hdf5(path):
+        if len(shape) != 4:
+            raise SystemExit("EMD output holds 4-D datacubes (mpi.py:440-498); write 3-D results as .npy")
+        create_emd(path, shape)
+        return None
     return np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=tuple(shape))
 
 
 def write_block(path, slices, block):
+    if is_hdf5(path):
+        import h5py
+        with h5py.File(path, "r+") as f:                      # dset.write_direct(recon, ...) of mpi.py:493-497
+            f["4DSTEM_experiment/data/datacubes/datacube_0/data"][slices] = block
+        return
     out = np.load(path, mmap_mode="r+")
     out[slices] = block
     out.flush()
@@ -139,7 +186,10 @@ def main(argv=None):
         recon, bn, dl = tv.denoise4D(block, mu, iterations=iterations, FISTA=fista, stopping_relative_change=args.stop,
                                      lam=lam, quiet=True, out=out, timing=tm, devices=list(range(args.devices)),
                                      schedule="streamed" if args.schedule == "streamed" else None)
-        out.flush()
+        if out is None:
+            write_block(args.output[0], tuple(slice(None) for _ in range(ndim)), recon)
+        else:
+            out.flush()
         say(f"{args.devices} devices from one process, schedule: {tm.get('schedule')}")
         world = args.devices
     elif world == 1:
@@ -153,7 +203,10 @@ def main(argv=None):
         kw = dict(iterations=iterations, FISTA=fista, stopping_relative_change=args.stop, lam=lam, quiet=True,
                   schedule=None if args.schedule == "auto" else args.schedule, out=out, timing=tm)
         recon, bn, dl = fn(block, mu, **kw)
-        out.flush()
+        if out is None:
+            write_block(args.output[0], tuple(slice(None) for _ in range(ndim)), recon)
+        else:
+            out.flush()
         say(f"schedule: {tm.get('schedule')}" + (f", {tm['stream_tiles']} tiles" if tm.get("stream_tiles") else ""))
     else:
         if ndim != 4:
@@ -182,8 +235,14 @@ def main(argv=None):
             if head:
                 create_output(args.output[0], data.shape)
             dist.barrier()
-            write_block(args.output[0], plan.owned_global, owned)
-            dist.barrier()
+            if is_hdf5(args.output[0]):
+                for r in range(world):                        # serial HDF5: one writer at a time (the reference uses mpio)
+                    if r == rank:
+                        write_block(args.output[0], plan.owned_global, owned)
+                    dist.barrier()
+            else:
+                write_block(args.output[0], plan.owned_global, owned)
+                dist.barrier()
         finally:
             dist.destroy_process_group()
     n = int(np.count_nonzero(dl)) if len(dl) else 0

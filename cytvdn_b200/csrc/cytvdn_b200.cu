@@ -276,6 +276,10 @@ int make_sweep(const Dims &D, int vw, size_t elem, const cytvdn_step_opts *o, in
 
 template <typename T> constexpr int vec_width() { return 16 / (int)sizeof(T); }
 
+// The reference's comparison-based clip leaves a value unchanged when the THRESHOLD is NaN (both comparisons are
+// false); +inf does the same and lets the float kernels clip with max.NaN / min.NaN.
+template <typename T> T clip_for_kernel(double c) { return std::isnan(c) ? (T)INFINITY : (T)c; }
+
 // Elements per thread: 16-byte vectors when every row start is 16-byte aligned (extent of the fast axis a
 // multiple of the vector width and all base pointers aligned); 8-byte vectors for float rows of even length;
 // else scalar.  `ptr_bits` = OR of all base pointers of the launch.
@@ -357,7 +361,7 @@ int run_acc(const AccCall &c)
     int nax = 0;
     for (int k = 0; k < 4; ++k) {
         const bool on = c.mode == ACC_ALL4 ? true : c.mode == ACC_ALL3 ? (k != 2) : ((c.axmask >> k) & 1);
-        P.clip[k] = (T)c.clip[k];
+        P.clip[k] = clip_for_kernel<T>(c.clip[k]);
         P.bc[k] = c.bc[k];
         if (!on) continue;
         ++nax;
@@ -498,7 +502,7 @@ int run_fused(const FusedCall &c)
         pb |= bits(c.bin[k]) | bits(c.bout[k]) | (c.fista ? (bits(c.din[k]) | bits(c.dout[k])) : 0);
         P.bin[k] = (const T *)c.bin[k]; P.bout[k] = (T *)c.bout[k];
         P.din[k] = (const T *)c.din[k]; P.dout[k] = (T *)c.dout[k];
-        P.clip[k] = (T)c.clip[k]; P.w[k] = (T)c.w[k]; P.bc[k] = c.bc[k];
+        P.clip[k] = clip_for_kernel<T>(c.clip[k]); P.w[k] = (T)c.w[k]; P.bc[k] = c.bc[k];
     }
     if (c.uin == c.uout) return fail(CYTVDN_E_INVALID, "the fused iteration is out of place: recon_in == recon_out");
     const int vw = pick_vw<T>(c.D.pitch, pb);

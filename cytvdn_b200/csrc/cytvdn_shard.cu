@@ -319,7 +319,7 @@ int cytvdn_shard_create(const cytvdn_shard_params *p, cytvdn_shard **out)
     return CYTVDN_OK;
 }
 
-int cytvdn_shard_destroy(cytvdn_shard *s)
+int cytvdn_shard_disconnect(cytvdn_shard *s)
 {
     if (!s) return CYTVDN_OK;
     DeviceGuard guard(s->device);
@@ -329,6 +329,15 @@ int cytvdn_shard_destroy(cytvdn_shard *s)
     if (s->lo.base && s->lo.ipc) cudaIpcCloseMemHandle(s->lo.base);
     if (s->hi.base && s->hi.ipc && !same) cudaIpcCloseMemHandle(s->hi.base);
     s->lo.base = s->hi.base = nullptr;
+    cudaGetLastError();
+    return CYTVDN_OK;
+}
+
+int cytvdn_shard_destroy(cytvdn_shard *s)
+{
+    if (!s) return CYTVDN_OK;
+    cytvdn_shard_disconnect(s);
+    DeviceGuard guard(s->device);
     for (auto e : s->pev) cudaEventDestroy(e);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
     for (auto ev : s->ev_pushed) if (ev) cudaEventDestroy(ev);

@@ -686,6 +686,21 @@ class EngineShard:
             self.lib.cytvdn_shard_destroy(self.h)
             self.h = C.c_void_p()
 
+    def close_collective(self, group=None):
+        """Tear-down on every rank of a process group: an arena a neighbour still has mapped through CUDA IPC stays
+        allocated until that neighbour unmaps it, so all ranks first unmap (disconnect), then free (destroy)."""
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if self.h:
+            self.lib.cytvdn_shard_synchronize(self.h)
+        if multi:
+            dist.barrier(group=group)          # nobody unmaps / frees an arena a neighbour still pushes into
+        if self.h:
+            self.lib.cytvdn_shard_disconnect(self.h)
+        if multi:
+            dist.barrier(group=group)          # every mapping of every arena is gone: cudaFree really frees
+        self.close()
+
 
 def _split_iterations(iterations, FISTA):
     if type(iterations) in (list, tuple):
@@ -767,12 +782,15 @@ def denoise4D_engine(block, mu, iterations=10, FISTA=True, stopping_relative_cha
         engine.store(out)
         if world > 1:
             dist.barrier(group=group)          # nobody frees (or re-loads) an arena a neighbour still pushes into
+        if own_engine and not return_engine:
+            engine.close_collective(group)
         if return_engine:
             return out, b_norm, delta, engine
         return out, b_norm, delta
-    finally:
-        if own_engine and not return_engine:
-            engine.close()
+    except BaseException:
+        if own_engine:
+            engine.close()                     # error path: no collective tear-down (the other ranks may be gone)
+        raise
 
 
 def emulate_engine_on_one_device(gdata, mu, world, iterations=10, FISTA=True, periodic=False, lam=None):

@@ -309,7 +309,8 @@ int cytvdn_stream_plan_sharded(const cytvdn_denoise_params *params, int64_t budg
  *
  * Use (every rank, or a loop over the ranks in one process):
  *   create -> export -> [exchange the 128-byte handles] -> connect(0, lower's handle), connect(1, upper's handle)
- *   -> load(block) -> iterate(nF, nU) [-> iterate ...] -> sums / store -> [all ranks synchronised] -> destroy.
+ *   -> load(block) -> iterate(nF, nU) [-> iterate ...] -> sums / store -> [all ranks synchronised] -> disconnect ->
+ *   [barrier] -> destroy.
  * All ranks must enqueue the same iterations.  A shard may be re-loaded and re-run any number of times; all ranks
  * must have finished (cytvdn_shard_synchronize + a barrier of the caller's) before any of them is destroyed.
  * ---------------------------------------------------------------------------------------------------------------
@@ -330,6 +331,10 @@ typedef struct cytvdn_shard_params {
 } cytvdn_shard_params;
 
 int cytvdn_shard_create(const cytvdn_shard_params *params, cytvdn_shard **shard);
+/* Tear-down, one process per GPU: an arena that a neighbour still has mapped (CUDA IPC) is not given back to the device
+   by cudaFree until that neighbour unmaps it.  So: all ranks synchronise, barrier, every rank DISCONNECTS (unmaps its
+   neighbours' arenas), barrier, every rank DESTROYS.  destroy alone also disconnects, which is enough in one process. */
+int cytvdn_shard_disconnect(cytvdn_shard *shard);
 int cytvdn_shard_destroy(cytvdn_shard *shard);
 /* out12 = { stored planes, first owned local plane, one past the last owned local plane, owned global range lo, hi,
    global index of local plane 0 (-1 / wraps on a periodic axis), has lower neighbour, has upper neighbour, arena

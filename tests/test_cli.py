@@ -72,3 +72,82 @@ def test_cli_single_gpu_matches_api(tmp_path):
         del os.environ["CYTVDN_STREAM_BUDGET_MB"]
     ref = tv.denoise4D(big, mu, 11, True, lam=lam, quiet=True)[0]
     assert np.array_equal(np.load(dst), ref)
+
+
+class _FakeH5:
+    """Just enough of h5py (File / Group / Dataset / attrs) to record what the EMD writer creates.  h5py itself is
+    not installed in this image; the test pins the layout of `mpi.py:440-498`, not HDF5."""
+    STORE = {}
+
+    class _Attrs(dict):
+        def create(self, k, v):
+            self[k] = v
+
+    class _Node:
+        def __init__(self, store, path):
+            self.store, self.path = store, path
+            self.attrs = store.setdefault(("attrs", path), _FakeH5._Attrs())
+
+        def create_group(self, name):
+            p = f"{self.path}/{name}".lstrip("/")
+            self.store[("group", p)] = True
+            return _FakeH5._Node(self.store, p)
+
+        def create_dataset(self, name, shape, dtype="float32"):
+            p = f"{self.path}/{name}".lstrip("/")
+            self.store[("data", p)] = np.zeros(shape, dtype=dtype)
+            return _FakeH5._Dset(self.store, p)
+
+        def __getitem__(self, name):
+            p = f"{self.path}/{name}".lstrip("/")
+            return _FakeH5._Dset(self.store, p) if ("data", p) in self.store else _FakeH5._Node(self.store, p)
+
+    class _Dset(_Node):
+        def __setitem__(self, sl, v):
+            self.store[("data", self.path)][sl] = v
+
+        @property
+        def shape(self):
+            return self.store[("data", self.path)].shape
+
+    class File(_Node):
+        def __init__(self, path, mode="r", **kw):
+            if mode == "w":
+                _FakeH5.STORE[path] = {}
+            super().__init__(_FakeH5.STORE[path], "")
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+
+def test_emd_writer_layout_with_fake_h5py(tmp_path, monkeypatch):
+    """`-o x.emd`: the EMD v0.7 group structure the reference hard-codes (`mpi.py:440-490`) and block-wise writes of
+    the owned tiles (`:493-497`), exercised through a stand-in for h5py."""
+    import sys
+    monkeypatch.setitem(sys.modules, "h5py", _FakeH5)
+    dst = str(tmp_path / "out.emd")
+    g = np.arange(11 * 7 * 4 * 6, dtype=np.float32).reshape(11, 7, 4, 6)
+    assert cli.create_output(dst, g.shape) is None
+    for rank in range(3):
+        p = ShardPlan(g.shape, 3, rank)
+        cli.write_block(dst, p.owned_global, g[p.owned_global])
+    st = _FakeH5.STORE[dst]
+    top = st[("attrs", "4DSTEM_experiment")]
+    assert (top["emd_group_type"], top["version_major"], top["version_minor"]) == (2, 0, 7)
+    for grp in ("metadata", "data", "data/datacubes", "data/counted_datacubes", "data/diffractionslices", "data/realslices",
+                "data/pointlists", "data/pointlistarrays", "data/datacubes/datacube_0"):
+        assert ("group", "4DSTEM_experiment/" + grp) in st, grp
+    dc = "4DSTEM_experiment/data/datacubes/datacube_0"
+    assert st[("attrs", dc)]["emd_group_type"] == 1 and st[("attrs", dc)]["metadata"] == -1
+    assert np.array_equal(st[("data", dc + "/data")], g) and st[("data", dc + "/data")].dtype == np.float32
+    for k, (n, label) in enumerate(zip(g.shape, (b"R_x", b"R_y", b"Q_x", b"Q_y")), start=1):
+        assert np.array_equal(st[("data", f"{dc}/dim{k}")], np.arange(n))
+        assert st[("attrs", f"{dc}/dim{k}")]["name"] == label and st[("attrs", f"{dc}/dim{k}")]["units"] == b"[pix]"
+    with pytest.raises(SystemExit, match="4-D"):
+        cli.create_output(dst, (4, 5, 6))
+    monkeypatch.setitem(sys.modules, "h5py", None)           # import h5py -> ImportError
+    with pytest.raises(SystemExit, match="needs h5py"):
+        cli.create_output(dst, g.shape)
