@@ -111,6 +111,7 @@ PROTOTYPES = {
     "cytvdn_shard_connect": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_ubyte)]),
     "cytvdn_shard_load": (C.c_int, [_vp, _vp]),
     "cytvdn_shard_iterate": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "cytvdn_shard_run_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "cytvdn_shard_synchronize": (C.c_int, [_vp]),
     "cytvdn_shard_sums": (C.c_int, [_vp, _dp, C.c_int]),
     "cytvdn_shard_store": (C.c_int, [_vp, _vp]),

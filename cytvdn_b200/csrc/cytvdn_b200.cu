@@ -2148,6 +2148,7 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int warm_workspace(cudaStream_t stream) { Workspace w; return get_workspace(stream, &w); }
 int pinned_alloc(void **out, size_t bytes) { return ::pinned_alloc(out, bytes); }
 int pinned_free(void *p) { return ::pinned_free(p); }
 }  // namespace cytvdn_internal

@@ -50,33 +50,45 @@ using cytvdn_internal::fail;
 
 namespace {
 
-constexpr int kSlots = 4;                 // launches per iteration that write sums (<= 3 used), 4 doubles each
+constexpr int kMaxBox = 16;               // boxes of scan axis 1 in the host-pipelined run
+constexpr int kSlots = 3 * kMaxBox;       // launches per iteration that write sums (3 per box), 4 doubles each
 constexpr size_t kAlign = 256;
 constexpr int kProfileMax = 256;          // iterations with per-phase events (cytvdn_shard_timeline)
-constexpr uint32_t kFlagLo = 0, kFlagHi = 1, kFlagErr = 2;     // header words
+// header words: "planes of iteration < value have landed" counters, raised by the neighbours
+//   [0] whole planes from the lower neighbour, [1] ... from the upper neighbour, [2] error,
+//   [4 + c] box c from the lower neighbour, [4 + kMaxBox + c] box c from the upper neighbour
+constexpr uint32_t kFlagLo = 0, kFlagHi = 1, kFlagErr = 2, kBoxLo = 4, kBoxHi = 4 + kMaxBox, kFlagWords = 4 + 2 * kMaxBox;
 
 inline size_t up(size_t x) { return (x + kAlign - 1) & ~(kAlign - 1); }
 
-// Spin until *flag >= want, modulo 2^16 (raised by a neighbour's copy engine; neighbours are never more than two
-// iterations apart).  One warp; gives up after ~20 s of SM clock and
-// records the failure in *err so that a dead neighbour cannot hang the GPU.
-__global__ void wait_flag_kernel(const volatile uint32_t *flag, uint32_t want, uint32_t *err)
+// Spin until, for every box c in [c_lo, c_hi], the neighbour's planes of the iteration before `want` have landed:
+// the whole-plane counter or the box's own counter has reached `want` (each raised by the neighbour's copy stream
+// behind the data).  One warp, one lane per box; gives up after ~20 s of SM clock and records the failure in *err so
+// that a dead neighbour cannot hang the GPU.
+__global__ void wait_flags_kernel(const volatile uint32_t *whole, const volatile uint32_t *box, int c_lo, int c_hi, uint32_t want,
+                                  uint32_t *err)
 {
-    if (threadIdx.x != 0) return;
-    const long long t0 = clock64();
-    uint32_t v;
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (((v - want) & 0xffffu) < 0x8000u) break;           // iteration numbers travel modulo 2^16
-        if (clock64() - t0 > 40000000000ll) { atomicExch(err, want ? want : 1u); break; }
-        __nanosleep(200);
+    const int c = c_lo + (int)threadIdx.x;
+    if (c <= c_hi) {
+        const long long t0 = clock64();
+        for (;;) {
+            uint32_t v, w;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(whole) : "memory");
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(w) : "l"(box + c) : "memory");
+            if ((int32_t)(v - want) >= 0 || (int32_t)(w - want) >= 0) break;
+            if (clock64() - t0 > 40000000000ll) { atomicExch(err, want ? want : 1u); break; }
+            __nanosleep(200);
+        }
     }
     __threadfence_system();
 }
 
-__global__ void fill_iota_kernel(uint32_t *p, uint32_t n)
+// raise a counter in the NEIGHBOUR's header (peer pointer); runs on the copy stream behind the plane it announces
+__global__ void set_flag_kernel(uint32_t *flag, uint32_t value)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+    __threadfence_system();
+    *(volatile uint32_t *)flag = value;
+    __threadfence_system();
 }
 
 struct Peer {
@@ -108,14 +120,18 @@ struct cytvdn_shard {
     char *arena = nullptr;
     size_t arena_bytes = 0, hdr = 0, pitch = 0;
     int n_arrays = 0;
-    uint32_t *flags = nullptr, *iota = nullptr;
+    uint32_t *flags = nullptr;
     double *sums = nullptr;                   // [max_iters][kSlots][4]
     Peer lo, hi;
     // ---- execution ----
-    cudaStream_t comp = nullptr, copy = nullptr;
-    cudaEvent_t ev_halo = nullptr, ev_pushed[2] = {nullptr, nullptr};
-    int64_t it_global = 0;                    // iterations enqueued since creation (flags count these)
-    int64_t it_run = 0;                       // ... since the last load
+    cudaStream_t comp = nullptr, copy = nullptr, up = nullptr, down = nullptr;     // up / down: host copies of run_host
+    cudaEvent_t ev_halo = nullptr;
+    cudaEvent_t ev_pushed[kMaxBox + 1][2] = {};      // [box (kMaxBox: whole planes)][iteration parity]
+    int64_t pushed_it[kMaxBox + 1][2];               // the iteration each was last recorded for (-1: never)
+    cudaEvent_t ev_up[kMaxBox] = {}, ev_box_done[kMaxBox] = {}, ev_down = nullptr;
+    int64_t it_global_base = 0;               // iterations enqueued since creation up to the last load (flags count
+    int64_t it_run = 0;                       // base + it_run); it_run: iterations since the last load
+    int64_t it_global() const { return it_global_base + it_run; }
     double tk = 1.0;
     bool profile = false;
     std::vector<cudaEvent_t> pev;             // kProfileMax x 6 events
@@ -160,31 +176,36 @@ void plan_1d(cytvdn_shard *s)
     s->own_hi = s->n_local - (s->has_hi ? 1 : 0);
 }
 
-int enqueue_iteration(cytvdn_shard *s, bool fista_it)
+// One step of the schedule: iteration `m_run` (counted from the last load) on the rows [j0, j1) of scan axis 1 --
+// the whole array (box < 0) or box `box` of a host-pipelined run.  Halo planes first, then the pushes of their rows on
+// the copy stream, then the interior planes.
+int enqueue_step(cytvdn_shard *s, int64_t m_run, bool fista_it, double tkr, int box, int nbox, int64_t j0, int64_t j1, bool zero_wrap1)
 {
-    if (s->it_run >= s->max_iters) return fail(CYTVDN_E_INVALID, "shard was created for %d iterations per load", s->max_iters);
-    const int64_t it = s->it_global;
+    const int64_t it = s->it_global_base + m_run;             // iteration number since creation (flags count these)
     const int in = (int)(it & 1), out = in ^ 1;
-    const bool first = s->it_run == 0;
-    double tkr = 0.0;
-    if (fista_it) {                                           // cyTVDN.py:154-156
-        const double tk_new = (1.0 + std::sqrt(1.0 + 4.0 * s->tk * s->tk)) / 2.0;
-        tkr = (s->tk - 1.0) / tk_new;
-        s->tk = tk_new;
-    }
-    const bool prof = s->profile && s->it_run < kProfileMax;
-    cudaEvent_t *pe = prof ? &s->pev[(size_t)s->it_run * 6] : nullptr;
+    const bool first = m_run == 0;
+    const bool whole = box < 0;
+    const int eb = whole ? kMaxBox : box;                     // index into the push events
+    const bool prof = s->profile && whole && m_run < kProfileMax;
+    cudaEvent_t *pe = prof ? &s->pev[(size_t)m_run * 6] : nullptr;
     if (prof) CYTVDN_CUDA_TRY(cudaEventRecord(pe[0], s->comp));
-    // ---- wait for the planes of the previous iteration (they went into the set this iteration reads).  Also at the
-    //      first iteration after a re-load: a neighbour that has raised our flag to `it` has swept its halo planes of
-    //      iteration it-1, the last readers of what our first push will overwrite. ----
-    if (it > 0) {
-        if (s->has_lo) wait_flag_kernel<<<1, 32, 0, s->comp>>>(s->flags + kFlagLo, (uint32_t)it, s->flags + kFlagErr);
-        if (s->has_hi) wait_flag_kernel<<<1, 32, 0, s->comp>>>(s->flags + kFlagHi, (uint32_t)it, s->flags + kFlagErr);
+    // ---- wait for the planes of the previous iteration (they went into the set this iteration reads); a box also
+    //      reads one row of each neighbouring box on the overlap planes.  Also at the first iteration after a re-load:
+    //      a neighbour that has raised our counter to `it` has swept its halo planes of iteration it-1, the last
+    //      readers of what our first push will overwrite. ----
+    if (it > 0 && (s->has_lo || s->has_hi)) {
+        const int c_lo = whole ? 0 : std::max(0, box - 1), c_hi = whole ? nbox - 1 : std::min(nbox - 1, box + 1);
+        if (s->has_lo)
+            wait_flags_kernel<<<1, 32, 0, s->comp>>>(s->flags + kFlagLo, s->flags + kBoxLo, c_lo, c_hi, (uint32_t)it, s->flags + kFlagErr);
+        if (s->has_hi)
+            wait_flags_kernel<<<1, 32, 0, s->comp>>>(s->flags + kFlagHi, s->flags + kBoxHi, c_lo, c_hi, (uint32_t)it, s->flags + kFlagErr);
         CYTVDN_CUDA_TRY(cudaGetLastError());
     }
-    // this iteration overwrites the set whose halo planes the copy engines read two iterations ago
-    if (s->it_run >= 2 && (s->has_lo || s->has_hi)) CYTVDN_CUDA_TRY(cudaStreamWaitEvent(s->comp, s->ev_pushed[it & 1], 0));
+    // this step overwrites planes of the set that the copy engines read two iterations ago
+    if (s->has_lo || s->has_hi)
+        for (int q = 0; q <= kMaxBox; ++q)
+            if (s->pushed_it[q][it & 1] == it - 2 && (whole || q == kMaxBox || q == box))
+                CYTVDN_CUDA_TRY(cudaStreamWaitEvent(s->comp, s->ev_pushed[q][it & 1], 0));
     if (prof) CYTVDN_CUDA_TRY(cudaEventRecord(pe[1], s->comp));
 
     int64_t shape[4] = {s->n_local, s->g[1], s->g[2], s->g[3]};
@@ -197,15 +218,17 @@ int enqueue_iteration(cytvdn_shard *s, bool fista_it)
     }
     const void *uin = first ? s->array(0) : s->array(s->idx_recon(in));       // recon = datacube.copy(), cyTVDN.py:145
     void *uout = s->array(s->idx_recon(out));
-    double *sums = s->sums + (size_t)s->it_run * kSlots * 4;
+    double *sums = s->sums + (size_t)m_run * kSlots * 4 + (size_t)(whole ? 0 : box) * 3 * 4;
 
     cytvdn_step_opts o;
     memset(&o, 0, sizeof o);
     o.row_pitch = s->n3p;
     o.own_lo[0] = s->own_lo; o.own_hi[0] = s->own_hi;
+    o.box_lo[1] = j0; o.box_hi[1] = j1;
     o.flags = 2;                                              // recon is stored for owned voxels only
     if (s->periodic && s->world > 1) o.flags |= 1 << 8;       // the wrap of axis 0 is the exchange's job
     if (!s->periodic && !s->mirror && s->has_lo && !s->has_hi) o.zero_wrap_mask = 1;   // global upper edge
+    if (zero_wrap1) o.zero_wrap_mask |= 2;                    // last box of a pipelined run: row 0 is iterations ahead
     auto sweep = [&](int64_t lo, int64_t hi, int slot) -> int {
         if (hi <= lo) return CYTVDN_OK;
         cytvdn_step_opts ob = o;
@@ -215,7 +238,7 @@ int enqueue_iteration(cytvdn_shard *s, bool fista_it)
                                       fista_it ? dout : nullptr, tkr, s->clip, s->w, s->periodic ? 0 : (s->mirror ? 3 : 2), sums + slot * 4,
                                       &ob, s->comp);
     };
-    CYTVDN_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * kSlots * 4, s->comp));
+    if (whole || box == 0) CYTVDN_CUDA_TRY(cudaMemsetAsync(s->sums + (size_t)m_run * kSlots * 4, 0, sizeof(double) * kSlots * 4, s->comp));
     // ---- halo planes first: the planes that travel and the upper overlap plane; the lower overlap plane is never
     //      swept (nothing owned depends on its accumulators, its recon is received) ----
     const int64_t n = s->n_local;
@@ -231,26 +254,44 @@ int enqueue_iteration(cytvdn_shard *s, bool fista_it)
         CYTVDN_CUDA_TRY(cudaStreamWaitEvent(s->copy, s->ev_halo, 0));
         if (prof) CYTVDN_CUDA_TRY(cudaEventRecord(pe[4], s->copy));
         const char *mine = s->array(s->idx_recon(out));
-        const uint32_t *val = s->iota + ((it + 1) & 0xffff);  // flags carry the iteration number modulo 2^32; the
-                                                              // source table holds 65536 consecutive values per epoch
+        const size_t row_b = (size_t)s->g[2] * s->n3p * s->elem;                 // one row of scan axis 1 inside a plane
+        const size_t off = (size_t)j0 * row_b, bytes = (size_t)(j1 - j0) * row_b;
         if (s->has_lo) {                                      // my first owned plane -> lower neighbour's LAST plane
             const Peer &p = s->lo;
-            char *dst = p.base + p.hdr + (size_t)s->idx_recon(out) * p.pitch + (size_t)(p.n_local - 1) * s->plane_b;
-            CYTVDN_CUDA_TRY(cudaMemcpyAsync(dst, mine + (size_t)s->own_lo * s->plane_b, s->plane_b, cudaMemcpyDeviceToDevice, s->copy));
-            CYTVDN_CUDA_TRY(cudaMemcpyAsync(p.base + sizeof(uint32_t) * kFlagHi, val, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->copy));
+            char *dst = p.base + p.hdr + (size_t)s->idx_recon(out) * p.pitch + (size_t)(p.n_local - 1) * s->plane_b + off;
+            CYTVDN_CUDA_TRY(cudaMemcpyAsync(dst, mine + (size_t)s->own_lo * s->plane_b + off, bytes, cudaMemcpyDeviceToDevice, s->copy));
+            set_flag_kernel<<<1, 1, 0, s->copy>>>((uint32_t *)p.base + (whole ? kFlagHi : kBoxHi + box), (uint32_t)(it + 1));
         }
         if (s->has_hi) {                                      // my last owned plane -> upper neighbour's plane 0
             const Peer &p = s->hi;
-            char *dst = p.base + p.hdr + (size_t)s->idx_recon(out) * p.pitch;
-            CYTVDN_CUDA_TRY(cudaMemcpyAsync(dst, mine + (size_t)(s->own_hi - 1) * s->plane_b, s->plane_b, cudaMemcpyDeviceToDevice, s->copy));
-            CYTVDN_CUDA_TRY(cudaMemcpyAsync(p.base + sizeof(uint32_t) * kFlagLo, val, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->copy));
+            char *dst = p.base + p.hdr + (size_t)s->idx_recon(out) * p.pitch + off;
+            CYTVDN_CUDA_TRY(cudaMemcpyAsync(dst, mine + (size_t)(s->own_hi - 1) * s->plane_b + off, bytes, cudaMemcpyDeviceToDevice, s->copy));
+            set_flag_kernel<<<1, 1, 0, s->copy>>>((uint32_t *)p.base + (whole ? kFlagLo : kBoxLo + box), (uint32_t)(it + 1));
         }
-        CYTVDN_CUDA_TRY(cudaEventRecord(s->ev_pushed[it & 1], s->copy));
+        CYTVDN_CUDA_TRY(cudaGetLastError());
+        CYTVDN_CUDA_TRY(cudaEventRecord(s->ev_pushed[eb][it & 1], s->copy));
+        s->pushed_it[eb][it & 1] = it;
         if (prof) CYTVDN_CUDA_TRY(cudaEventRecord(pe[5], s->copy));
     }
     if (int rc = sweep(lo_end, hi_begin, 2)) return rc;       // interior, under the exchange
     if (prof) CYTVDN_CUDA_TRY(cudaEventRecord(pe[3], s->comp));
-    ++s->it_global;
+    return CYTVDN_OK;
+}
+
+// the FISTA ratio of the next iteration (cyTVDN.py:154-156), host float64
+double next_tk_ratio(cytvdn_shard *s)
+{
+    const double tk_new = (1.0 + std::sqrt(1.0 + 4.0 * s->tk * s->tk)) / 2.0;
+    const double r = (s->tk - 1.0) / tk_new;
+    s->tk = tk_new;
+    return r;
+}
+
+int enqueue_iteration(cytvdn_shard *s, bool fista_it)
+{
+    if (s->it_run >= s->max_iters) return fail(CYTVDN_E_INVALID, "shard was created for %d iterations per load", s->max_iters);
+    const double tkr = fista_it ? next_tk_ratio(s) : 0.0;
+    if (int rc = enqueue_step(s, s->it_run, fista_it, tkr, -1, 1, 0, s->g[1], false)) return rc;
     ++s->it_run;
     return CYTVDN_OK;
 }
@@ -287,8 +328,8 @@ int cytvdn_shard_create(const cytvdn_shard_params *p, cytvdn_shard **out)
     DeviceGuard guard(dev);
     s->n_arrays = 1 + 2 * s->per();
     s->pitch = up((size_t)s->n_local * s->plane_b);
-    const size_t flags_b = up(64), iota_b = up(sizeof(uint32_t) * 65536), sums_b = up(sizeof(double) * kSlots * 4 * s->max_iters);
-    s->hdr = flags_b + iota_b + sums_b;
+    const size_t flags_b = up(sizeof(uint32_t) * kFlagWords), sums_b = up(sizeof(double) * kSlots * 4 * s->max_iters);
+    s->hdr = flags_b + sums_b;
     s->arena_bytes = s->hdr + (size_t)s->n_arrays * s->pitch;
     cudaError_t e = cudaMalloc((void **)&s->arena, s->arena_bytes);
     if (e != cudaSuccess) {
@@ -298,8 +339,8 @@ int cytvdn_shard_create(const cytvdn_shard_params *p, cytvdn_shard **out)
         return fail(CYTVDN_E_NOMEM, "cudaMalloc of the shard arena (%zu bytes) failed: %s", need, cudaGetErrorString(e));
     }
     s->flags = (uint32_t *)s->arena;
-    s->iota = (uint32_t *)(s->arena + flags_b);
-    s->sums = (double *)(s->arena + flags_b + iota_b);
+    s->sums = (double *)(s->arena + flags_b);
+    for (auto &q : s->pushed_it) q[0] = q[1] = -1;
     auto bail = [&](cudaError_t err, const char *what) {
         cudaGetLastError();
         cudaFree(s->arena);
@@ -308,13 +349,23 @@ int cytvdn_shard_create(const cytvdn_shard_params *p, cytvdn_shard **out)
     };
     if ((e = cudaStreamCreateWithFlags(&s->comp, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&s->up, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&s->down, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    for (auto &ev : s->ev_pushed)
-        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&s->ev_down, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for (auto &q : s->ev_pushed)
+        for (auto &ev : q)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for (int c = 0; c < kMaxBox; ++c) {
+        if ((e = cudaEventCreateWithFlags(&s->ev_up[c], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&s->ev_box_done[c], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    }
     if ((e = cudaMemsetAsync(s->arena, 0, s->hdr, s->comp)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
-    fill_iota_kernel<<<64, 256, 0, s->comp>>>(s->iota, 65536u);
     // plane 0 of the accumulators is never swept on a shard with a lower neighbour: keep it defined in both sets
     if ((e = cudaStreamSynchronize(s->comp)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
+    // the sweeps' reduction scratch now, not at the first launch: an allocation in the middle of a run may synchronise
+    // the device while another shard's wait kernel spins on it (several shards of one process on one GPU)
+    if (cytvdn_internal::warm_workspace(s->comp) != CYTVDN_OK) { cudaFree(s->arena); delete s; return CYTVDN_E_CUDA; }
     *out = s;
     return CYTVDN_OK;
 }
@@ -323,8 +374,7 @@ int cytvdn_shard_disconnect(cytvdn_shard *s)
 {
     if (!s) return CYTVDN_OK;
     DeviceGuard guard(s->device);
-    if (s->comp) cudaStreamSynchronize(s->comp);
-    if (s->copy) cudaStreamSynchronize(s->copy);
+    for (cudaStream_t st : {s->comp, s->copy, s->up, s->down}) if (st) cudaStreamSynchronize(st);
     const bool same = s->lo.base && s->lo.base == s->hi.base;                     // one mapping, two roles
     if (s->lo.base && s->lo.ipc) cudaIpcCloseMemHandle(s->lo.base);
     if (s->hi.base && s->hi.ipc && !same) cudaIpcCloseMemHandle(s->hi.base);
@@ -340,9 +390,14 @@ int cytvdn_shard_destroy(cytvdn_shard *s)
     DeviceGuard guard(s->device);
     for (auto e : s->pev) cudaEventDestroy(e);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
-    for (auto ev : s->ev_pushed) if (ev) cudaEventDestroy(ev);
+    if (s->ev_down) cudaEventDestroy(s->ev_down);
+    for (auto &q : s->ev_pushed) for (auto ev : q) if (ev) cudaEventDestroy(ev);
+    for (auto ev : s->ev_up) if (ev) cudaEventDestroy(ev);
+    for (auto ev : s->ev_box_done) if (ev) cudaEventDestroy(ev);
     if (s->comp) cudaStreamDestroy(s->comp);
     if (s->copy) cudaStreamDestroy(s->copy);
+    if (s->up) cudaStreamDestroy(s->up);
+    if (s->down) cudaStreamDestroy(s->down);
     if (s->arena) cudaFree(s->arena);
     cudaGetLastError();
     delete s;
@@ -417,13 +472,17 @@ int cytvdn_shard_array(const cytvdn_shard *s, int which, int set, int axis, void
 {
     if (!s || !ptr) return fail(CYTVDN_E_INVALID, "NULL argument");
     // `set` 0: the state the NEXT iteration reads (current), 1: the other one
-    const int cur = (int)((s->it_global & 1) ^ (set ? 1 : 0));
+    const int cur = (int)((s->it_global() & 1) ^ (set ? 1 : 0));
     if (which == 0) *ptr = s->array(0);
     else if (which == 1) *ptr = (s->it_run == 0 && !set) ? s->array(0) : s->array(s->idx_recon(cur));
     else if (which == 2 && axis >= 0 && axis < 4) *ptr = s->array(s->idx_b(cur, axis));
     else if (which == 3 && axis >= 0 && axis < 4 && s->fista) *ptr = s->array(s->idx_d(cur, axis));
     else return fail(CYTVDN_E_INVALID, "which must be 0 (orig), 1 (recon), 2 (b), 3 (d); axis 0..3");
     return CYTVDN_OK;
+}
+
+namespace {
+int reset_state(cytvdn_shard *s);
 }
 
 int cytvdn_shard_load(cytvdn_shard *s, const void *block)
@@ -433,8 +492,7 @@ int cytvdn_shard_load(cytvdn_shard *s, const void *block)
     if (s->has_hi && !s->hi.base) return fail(CYTVDN_E_INVALID, "upper neighbour not connected");
     DeviceGuard guard(s->device);
     // the previous run's iterations (and the pushes they issued) are complete on this shard
-    CYTVDN_CUDA_TRY(cudaStreamSynchronize(s->comp));
-    CYTVDN_CUDA_TRY(cudaStreamSynchronize(s->copy));
+    for (cudaStream_t st : {s->comp, s->copy, s->up, s->down}) CYTVDN_CUDA_TRY(cudaStreamSynchronize(st));
     const size_t rows = (size_t)s->n_local * s->g[1] * s->g[2];
     if (block) {                                              // dense rows -> padded rows
         char *dst = s->array(0);
@@ -445,9 +503,15 @@ int cytvdn_shard_load(cytvdn_shard *s, const void *block)
                                               rows, cudaMemcpyDefault, s->comp));
         }
     }
+    return reset_state(s);
+}
+
+namespace {
+int reset_state(cytvdn_shard *s)
+{
     // b = d = 0 in the set the first iteration reads; plane 0 of the other set too (never swept with a lower
     // neighbour, so it must not hold garbage -- ADVICE round 1)
-    const int in = (int)(s->it_global & 1);
+    const int in = (int)(s->it_global() & 1);
     for (int k = 0; k < 4; ++k) {
         CYTVDN_CUDA_TRY(cudaMemsetAsync(s->array(s->idx_b(in, k)), 0, (size_t)s->n_local * s->plane_b, s->comp));
         CYTVDN_CUDA_TRY(cudaMemsetAsync(s->array(s->idx_b(in ^ 1, k)), 0, s->plane_b, s->comp));
@@ -456,8 +520,79 @@ int cytvdn_shard_load(cytvdn_shard *s, const void *block)
             CYTVDN_CUDA_TRY(cudaMemsetAsync(s->array(s->idx_d(in ^ 1, k)), 0, s->plane_b, s->comp));
         }
     }
+    s->it_global_base += s->it_run;           // the counters the neighbours raise keep counting across loads
     s->it_run = 0;
     s->tk = 1.0;
+    return CYTVDN_OK;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-pipelined run (one process per GPU, or any single shard): load from a HOST block, iterate, store the owned planes
+// to a HOST block, with the PCIe copies overlapped with the iterations -- the single-GPU wavefront pipeline of
+// cytvdn_denoise carried into the sharded loop.  Boxes are cut along scan axis 1, the axis that is NOT sharded, so the
+// wavefront over (box, iteration) runs in lockstep on all ranks and does not couple them; per box and iteration the
+// box's rows of the halo planes travel, announced by the box's own counter.  Box c starts iterating when boxes c and
+// c+1 have arrived and is copied back when ITS last iteration is done.  Needs a non-periodic boundary (box 0 would
+// depend on the last box), dense rows (a 2-D copy per box) and at least 4 rows of axis 1 per box.
+// ---------------------------------------------------------------------------------------------------------------
+int cytvdn_shard_run_host(cytvdn_shard *s, const void *block, void *owned_out, int n_fista, int n_plain)
+{
+    if (!s || !block || !owned_out || n_fista < 0 || n_plain < 0) return fail(CYTVDN_E_INVALID, "bad argument");
+    if (n_fista > 0 && !s->fista) return fail(CYTVDN_E_INVALID, "shard was created without FISTA auxiliaries");
+    const int n_it = n_fista + n_plain;
+    if (n_it > s->max_iters) return fail(CYTVDN_E_INVALID, "shard was created for %d iterations per load", s->max_iters);
+    if (s->has_lo && !s->lo.base) return fail(CYTVDN_E_INVALID, "lower neighbour not connected");
+    if (s->has_hi && !s->hi.base) return fail(CYTVDN_E_INVALID, "upper neighbour not connected");
+    int nbox = (int)std::min<int64_t>(kMaxBox, s->g[1] / 4);
+    { const char *env = getenv("CYTVDN_SHARD_PIPELINE"); if (env && *env) nbox = std::min(nbox, atoi(env)); }
+    if (s->periodic || s->n3p != s->n3 || nbox < 2 || n_it < 1) {     // not pipelined: plain load / iterate / store
+        if (int rc = cytvdn_shard_load(s, block)) return rc;
+        if (int rc = cytvdn_shard_iterate(s, n_fista, n_plain)) return rc;
+        return cytvdn_shard_store(s, owned_out);
+    }
+    DeviceGuard guard(s->device);
+    for (cudaStream_t st : {s->comp, s->copy, s->up, s->down}) CYTVDN_CUDA_TRY(cudaStreamSynchronize(st));
+    if (int rc = reset_state(s)) return rc;                   // (memsets on the compute stream, before the first sweep)
+    auto jlo = [&](int c) -> int64_t { return s->g[1] * c / nbox; };
+    const size_t row_b = (size_t)s->g[2] * s->n3 * s->elem;   // one row of scan axis 1 (dense == padded here)
+    const size_t dense_plane = (size_t)s->g[1] * row_b;
+    // ---- uploads: box by box, every stored plane's rows [j0, j1) in one 2-D copy ----
+    for (int c = 0; c < nbox; ++c) {
+        const size_t off = (size_t)jlo(c) * row_b, width = (size_t)(jlo(c + 1) - jlo(c)) * row_b;
+        CYTVDN_CUDA_TRY(cudaMemcpy2DAsync(s->array(0) + off, s->plane_b, (const char *)block + off, dense_plane, width,
+                                          (size_t)s->n_local, cudaMemcpyDefault, s->up));
+        CYTVDN_CUDA_TRY(cudaEventRecord(s->ev_up[c], s->up));
+    }
+    // ---- iterations: wavefront over (box, iteration) at both ends, whole-array sweeps in between ----
+    int64_t count = 0;
+    if (int rc = cytvdn_pipeline_schedule(nbox, n_it, nullptr, nullptr, 0, &count)) return rc;
+    std::vector<int32_t> obox((size_t)count), oit((size_t)count);
+    if (int rc = cytvdn_pipeline_schedule(nbox, n_it, obox.data(), oit.data(), count, &count)) return rc;
+    std::vector<double> tkr((size_t)n_it, 0.0);
+    for (int m = 0; m < n_fista; ++m) tkr[m] = next_tk_ratio(s);
+    const int cur_final = (int)((s->it_global_base + n_it) & 1);
+    for (int64_t q = 0; q < count; ++q) {
+        const int c = obox[q], m = oit[q];
+        if (c >= 0 && m == 0) CYTVDN_CUDA_TRY(cudaStreamWaitEvent(s->comp, s->ev_up[std::min(c + 1, nbox - 1)], 0));
+        if (c < 0 && m == 0) CYTVDN_CUDA_TRY(cudaStreamWaitEvent(s->comp, s->ev_up[nbox - 1], 0));
+        const bool last_box = c == nbox - 1;
+        if (int rc = enqueue_step(s, m, m < n_fista, tkr[m], c, nbox, c < 0 ? 0 : jlo(c), c < 0 ? s->g[1] : jlo(c + 1),
+                                  last_box && !s->mirror))
+            return rc;
+        if (m == n_it - 1) {                                  // this box (or everything) is final: copy its owned planes home
+            const int c0 = c < 0 ? 0 : c, c1 = c < 0 ? nbox : c + 1;
+            const size_t off = (size_t)jlo(c0) * row_b, width = (size_t)(jlo(c1) - jlo(c0)) * row_b;
+            CYTVDN_CUDA_TRY(cudaEventRecord(s->ev_box_done[c0], s->comp));
+            CYTVDN_CUDA_TRY(cudaStreamWaitEvent(s->down, s->ev_box_done[c0], 0));
+            const char *src = s->array(s->idx_recon(cur_final)) + (size_t)s->own_lo * s->plane_b + off;
+            CYTVDN_CUDA_TRY(cudaMemcpy2DAsync((char *)owned_out + off, dense_plane, src, s->plane_b, width,
+                                              (size_t)(s->own_hi - s->own_lo), cudaMemcpyDefault, s->down));
+        }
+    }
+    s->it_run = n_it;
+    CYTVDN_CUDA_TRY(cudaEventRecord(s->ev_down, s->down));
+    CYTVDN_CUDA_TRY(cudaStreamWaitEvent(s->comp, s->ev_down, 0));     // "everything this run enqueued" ends on comp
     return CYTVDN_OK;
 }
 
@@ -475,8 +610,7 @@ int cytvdn_shard_synchronize(cytvdn_shard *s)
 {
     if (!s) return fail(CYTVDN_E_INVALID, "NULL argument");
     DeviceGuard guard(s->device);
-    CYTVDN_CUDA_TRY(cudaStreamSynchronize(s->comp));
-    CYTVDN_CUDA_TRY(cudaStreamSynchronize(s->copy));
+    for (cudaStream_t st : {s->comp, s->copy, s->up, s->down}) CYTVDN_CUDA_TRY(cudaStreamSynchronize(st));
     uint32_t err = 0;
     CYTVDN_CUDA_TRY(cudaMemcpy(&err, s->flags + kFlagErr, sizeof err, cudaMemcpyDeviceToHost));
     if (err) return fail(CYTVDN_E_CUDA, "halo exchange timed out on rank %d waiting for iteration %u of a neighbour", s->rank, err);
@@ -511,7 +645,7 @@ int cytvdn_shard_store(cytvdn_shard *s, void *owned_block)
 {
     if (!s || !owned_block) return fail(CYTVDN_E_INVALID, "NULL argument");
     DeviceGuard guard(s->device);
-    const int cur = (int)(s->it_global & 1);
+    const int cur = (int)(s->it_global() & 1);
     const char *src = (s->it_run == 0 ? s->array(0) : s->array(s->idx_recon(cur))) + (size_t)s->own_lo * s->plane_b;
     const size_t rows = (size_t)(s->own_hi - s->own_lo) * s->g[1] * s->g[2];
     if (s->n3p == s->n3) CYTVDN_CUDA_TRY(cudaMemcpyAsync(owned_block, src, rows * s->n3 * s->elem, cudaMemcpyDefault, s->comp));
@@ -684,7 +818,7 @@ int cytvdn_denoise_sharded(const cytvdn_denoise_params *p, int ndev, const int *
     for (int r = 0; r < ndev; ++r) {
         cytvdn_shard *s = sh[r];
         DeviceGuard g(s->device);
-        const int cur = (int)(s->it_global & 1);
+        const int cur = (int)(s->it_global() & 1);
         const char *src = (s->it_run == 0 ? s->array(0) : s->array(s->idx_recon(cur))) + (size_t)s->own_lo * s->plane_b;
         char *dst = (char *)recon + (size_t)s->valid_lo * gplane;
         const size_t rows = (size_t)(s->own_hi - s->own_lo) * s->g[1] * s->g[2];

@@ -6,6 +6,8 @@ namespace cytvdn_internal {
 // records the calling thread's error message (cytvdn_last_error) and returns `code`
 int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 void count_launch();
+// create the reduction workspace of (current device, stream) now (its first use allocates, which may synchronise the device)
+int warm_workspace(cudaStream_t stream);
 // page-locked host memory with the huge-page allocator of cytvdn_host_alloc
 int pinned_alloc(void **out, size_t bytes);
 int pinned_free(void *p);

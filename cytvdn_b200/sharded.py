@@ -559,7 +559,9 @@ class EngineShard:
         lam = (mu * 1.0 / 32.0) if lam is None else np.asarray(lam, dtype=dt)      # cyTVDN.py:67-68
         P = _lib.ShardParams()
         P.dtype = 0 if dt == np.float32 else 1
-        P.world, P.rank, P.periodic, P.fista = int(world), int(rank), int(bool(periodic)), int(bool(fista))
+        # periodic: False / True (BC_mode 0 on the split axis), or 2 = the clamped mirror (BC_mode 3) at the global edges
+        P.world, P.rank, P.fista = int(world), int(rank), int(bool(fista))
+        P.periodic = 2 if (periodic is not True and periodic == 2) else int(bool(periodic))
         P.max_iters = max(1, int(max_iters))
         P.device = -1 if device is None else int(device)
         for k in range(4):
@@ -651,6 +653,15 @@ class EngineShard:
         torch.cuda.current_stream().synchronize()
         self.load(None)
 
+    def run_host(self, block, owned_out, n_fista=0, n_plain=0):
+        """``load`` + ``iterate`` + ``store`` with host arrays, PCIe copies overlapped with the iterations (boxes along
+        scan axis 1, wavefront over (box, iteration)); asynchronous: ``synchronize()`` / ``sums()`` wait for it."""
+        assert block.flags["C_CONTIGUOUS"] and block.dtype == self.dtype and tuple(block.shape) == self.local_shape
+        assert owned_out.flags["C_CONTIGUOUS"] and owned_out.dtype == self.dtype and tuple(owned_out.shape) == self.owned_shape
+        self._keep = (block, owned_out)
+        self._lib.check(self.lib.cytvdn_shard_run_host(self.h, C.c_void_p(block.ctypes.data), C.c_void_p(owned_out.ctypes.data),
+                                                       int(n_fista), int(n_plain)))
+
     def iterate(self, n_fista=0, n_plain=0):
         self._lib.check(self.lib.cytvdn_shard_iterate(self.h, int(n_fista), int(n_plain)))
 
@@ -739,12 +750,23 @@ def denoise4D_engine(block, mu, iterations=10, FISTA=True, stopping_relative_cha
             handles = [engine.export()]
         engine.connect_all(handles)
     try:
-        engine.load(block)
-        if world > 1:
-            dist.barrier(group=group)          # every rank's flags and state are in place before anyone pushes
         ran = np.zeros(n, dtype=bool)
         glob = np.zeros((max(n, 1), 3))
-        if stopping_relative_change is None:
+        # host arrays in and out, fixed iteration count: the library overlaps the PCIe copies with the iterations
+        # (wavefront over boxes of scan axis 1; no-op fall-back inside for periodic runs / padded rows)
+        piped = (not is_t) and stopping_relative_change is None and n > 0 and (out is None or not hasattr(out, "data_ptr"))
+        if piped:
+            if out is None:
+                out = np.empty(engine.owned_shape, dtype=dt)
+            engine.run_host(block, out, nF, nU)
+            ran[:] = True
+        else:
+            engine.load(block)
+            if world > 1:
+                dist.barrier(group=group)      # every rank's flags and state are in place before anyone pushes
+        if piped:
+            pass
+        elif stopping_relative_change is None:
             engine.iterate(nF, nU)
             ran[:] = True
         else:
@@ -776,10 +798,11 @@ def denoise4D_engine(block, mu, iterations=10, FISTA=True, stopping_relative_cha
         with np.errstate(all="ignore"):
             b_norm = np.where(ran, g[:n, 0], 0.0).astype(dt)
             delta = np.where(ran, g[:n, 1] / g[:n, 2], 0.0).astype(dt)
-        if out is None:
-            out = (torch.empty(engine.owned_shape, dtype=block.dtype, device=dev) if is_t
-                   else np.empty(engine.owned_shape, dtype=dt))
-        engine.store(out)
+        if not piped:
+            if out is None:
+                out = (torch.empty(engine.owned_shape, dtype=block.dtype, device=dev) if is_t
+                       else np.empty(engine.owned_shape, dtype=dt))
+            engine.store(out)
         if world > 1:
             dist.barrier(group=group)          # nobody frees (or re-loads) an arena a neighbour still pushes into
         if own_engine and not return_engine:

@@ -351,6 +351,12 @@ int cytvdn_shard_connect(cytvdn_shard *shard, int side, const unsigned char hand
 int cytvdn_shard_load(cytvdn_shard *shard, const void *block);
 /* enqueue n_fista FISTA iterations, then n_plain unaccelerated ones (returns at once) */
 int cytvdn_shard_iterate(cytvdn_shard *shard, int n_fista, int n_plain);
+/* load + iterate + store in one call, HOST blocks in and out, with the PCIe copies overlapped with the iterations: the
+   wavefront pipeline of cytvdn_denoise with boxes cut along scan axis 1 (the axis that is not sharded); per box and
+   iteration the box's rows of the halo planes travel.  block: stored planes (as for load), owned_out: owned planes,
+   both dense and preferably page-locked.  Asynchronous (cytvdn_shard_synchronize / _sums wait for it).  Falls back to
+   load / iterate / store for periodic runs, padded rows or fewer than 8 rows of axis 1.  Bit-identical results. */
+int cytvdn_shard_run_host(cytvdn_shard *shard, const void *block, void *owned_out, int n_fista, int n_plain);
 /* wait for everything this shard has enqueued; reports a halo wait that timed out (dead neighbour) */
 int cytvdn_shard_synchronize(cytvdn_shard *shard);
 /* out[i*3 + {0,1,2}] = this shard's sum|b|, sum|recon' - recon|, sum|recon| over OWNED voxels of iteration i < n

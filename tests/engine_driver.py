@@ -57,6 +57,38 @@ def one_device():
         print(json.dumps({"case": [list(shape), world, iters, periodic, dtype], "engine": ok1, "c_loop": ok2,
                           "ok": ok1 and ok2}), flush=True)
         bad += not (ok1 and ok2)
+    # host-pipelined run (cytvdn_shard_run_host): boxes along scan axis 1, wavefront over (box, iteration), per-box
+    # halo pushes and counters; every shard enqueues its whole run at once
+    for shape, world, iters, nbox, mirror in (((9, 16, 6, 8), 2, [7, 5], 4, False), ((13, 24, 5, 12), 3, 11, 6, False),
+                                              ((8, 12, 6, 8), 2, 3, 3, False), ((10, 16, 6, 8), 1, 9, 4, False),
+                                              ((9, 16, 6, 8), 3, [40, 3], 4, False), ((9, 16, 6, 8), 2, 9, 4, True)):
+        data = make(shape, "float32", 11)
+        mu = np.array([1, 1, .5, .5], dtype=np.float32)
+        bc = 3 if mirror else 2
+        ref = tv.denoise4D(data, mu, iters, True, BC_mode=bc, quiet=True)
+        nF, nU = (iters, 0) if isinstance(iters, int) else iters
+        os.environ["CYTVDN_SHARD_PIPELINE"] = str(nbox)
+        eng = [sharded.EngineShard(shape, world, r, mu, None, np.float32, fista=True, max_iters=nF + nU, periodic=2 if mirror else False)
+               for r in range(world)]
+        handles = [e.export() for e in eng]
+        outs = []
+        for e in eng:
+            e.connect_all(handles)
+        for e in eng:                                         # each shard's complete run is enqueued before the next one's
+            blk = np.ascontiguousarray(data[e.read_lo:e.read_lo + e.n_local])
+            out = np.empty(e.owned_shape, np.float32)
+            e.run_host(blk, out, nF, nU)
+            outs.append(out)
+        tot = np.zeros((nF + nU, 3))
+        for e in eng:
+            tot += e.sums(nF + nU)
+        got = np.concatenate(outs, axis=0)
+        for e in eng:
+            e.close()
+        del os.environ["CYTVDN_SHARD_PIPELINE"]
+        ok = bool(np.array_equal(got, ref[0])) and np.allclose(tot[:, 1] / tot[:, 2], ref[2].astype(np.float64), rtol=1e-4)
+        print(json.dumps({"case": ["run_host", list(shape), world, iters, nbox, mirror], "ok": ok}), flush=True)
+        bad += not ok
     # BC_mode=3 (clamped mirror) sharded: the mirror applies at the global edges only
     data = make((14, 6, 8, 12), "float32", 9)
     mu = np.array([1, 1, .5, .5], dtype=np.float32)
@@ -108,6 +140,21 @@ def ipc(share_gpu):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if rank == 0:
                 print(json.dumps({"case": [list(shape), world, iters, periodic, dtype], "ok": bool(flag.item())}), flush=True)
+            bad += not bool(flag.item())
+        # host arrays in and out: the pipelined run (boxes along scan axis 1) over real CUDA IPC
+        for shape, iters, nbox in (((11, 16, 6, 8), [7, 5], 4), ((9, 24, 5, 12), 40, 6), ((8, 12, 6, 8), 3, 3)):
+            data = make(shape, "float32", 11)
+            mu = np.array([1, 1, .5, .5], dtype=np.float32)
+            ref = tv.denoise4D(data, mu, iters, True, quiet=True)
+            plan = sharded.ShardPlan(shape, world, rank)
+            os.environ["CYTVDN_SHARD_PIPELINE"] = str(nbox)
+            own, bn, dl = sharded.denoise4D_engine(np.ascontiguousarray(plan.extract(data)), mu, iters, True, gshape=shape)
+            del os.environ["CYTVDN_SHARD_PIPELINE"]
+            ok = bool(np.array_equal(own, ref[0][plan.owned_global[0]])) and np.allclose(dl.astype(np.float64), ref[2].astype(np.float64), rtol=1e-4)
+            flag = torch.tensor([int(ok)], device=fdev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(json.dumps({"case": ["run_host", list(shape), world, iters, nbox], "ok": bool(flag.item())}), flush=True)
             bad += not bool(flag.item())
         data = make((12, 8, 8, 16), "float32", 5)
         mu = np.array([1, 1, .5, .5], dtype=np.float32)
