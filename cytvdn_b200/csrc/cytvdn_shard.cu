@@ -69,7 +69,7 @@ __global__ void wait_flags_kernel(const volatile uint32_t *whole, const volatile
                                   uint32_t *err)
 {
     const int c = c_lo + (int)threadIdx.x;
-    if (c <= c_hi) {
+    if (c <= c_hi && *(volatile uint32_t *)err == 0) {        // (after one timeout every later wait gives up at once)
         const long long t0 = clock64();
         for (;;) {
             uint32_t v, w;
@@ -340,7 +340,7 @@ int cytvdn_shard_create(const cytvdn_shard_params *p, cytvdn_shard **out)
     }
     s->flags = (uint32_t *)s->arena;
     s->sums = (double *)(s->arena + flags_b);
-    for (auto &q : s->pushed_it) q[0] = q[1] = -1;
+    for (auto &q : s->pushed_it) q[0] = q[1] = -100;
     auto bail = [&](cudaError_t err, const char *what) {
         cudaGetLastError();
         cudaFree(s->arena);

@@ -16,6 +16,9 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
+import signal
+signal.alarm(int(os.environ.get("ENGINE_DRIVER_ALARM", "240")))      # a dead-locked exchange must not hold the GPU box
+
 
 def cases_small():
     # (global shape, world, iterations, periodic, dtype)
@@ -74,11 +77,24 @@ def one_device():
         outs = []
         for e in eng:
             e.connect_all(handles)
-        for e in eng:                                         # each shard's complete run is enqueued before the next one's
-            blk = np.ascontiguousarray(data[e.read_lo:e.read_lo + e.n_local])
-            out = np.empty(e.owned_shape, np.float32)
-            e.run_host(blk, out, nF, nU)
-            outs.append(out)
+        # one host thread per shard, like one process per GPU: a shard's run is thousands of launches, and a host that
+        # blocks on a full launch queue must not keep the OTHER shards' pushes from being enqueued
+        import threading
+        outs = [np.empty(e.owned_shape, np.float32) for e in eng]
+        blks = [np.ascontiguousarray(data[e.read_lo:e.read_lo + e.n_local]) for e in eng]
+        errs = []
+
+        def work(k):
+            try:
+                eng[k].run_host(blks[k], outs[k], nF, nU)
+            except Exception as ex:
+                errs.append(repr(ex))
+        th = [threading.Thread(target=work, args=(k,)) for k in range(world)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        assert not errs, errs
         tot = np.zeros((nF + nU, 3))
         for e in eng:
             tot += e.sums(nF + nU)

@@ -30,7 +30,7 @@ def test_engine_all_ranks_on_one_device():
     flags, pushes and owned-only stores, and the C ABI's single-process loop `cytvdn_denoise_sharded`
     (`tv.denoise4D(devices=[0, 0, ...])`) -- uneven splits, one plane per rank, odd rows, periodic, hybrid counts,
     float64, early stopping."""
-    lines = _run([sys.executable, DRIVER, "one_device"])
+    lines = _run([sys.executable, DRIVER, "one_device"], timeout=300)
     assert len(lines) == 17
 
 
@@ -40,7 +40,7 @@ def test_engine_cuda_ipc_two_processes_sharing_a_gpu():
     ONE GPU (two contexts time-slice; gloo carries the handles), so the multi-process path is covered by the
     single-GPU tier too."""
     lines = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                  "--master-addr", "127.0.0.1", "--master-port", "29533", DRIVER, "ipc", "--share-gpu"], timeout=900)
+                  "--master-addr", "127.0.0.1", "--master-port", "29533", DRIVER, "ipc", "--share-gpu"], timeout=300)
     assert len(lines) >= 11
 
 
@@ -53,7 +53,7 @@ def test_engine_cuda_ipc_one_process_per_gpu():
         pytest.skip("needs at least 2 GPUs")
     world = 4 if n >= 4 else 2
     _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-          "--master-addr", "127.0.0.1", "--master-port", "29534", DRIVER, "ipc"], timeout=900)
+          "--master-addr", "127.0.0.1", "--master-port", "29534", DRIVER, "ipc"], timeout=300)
 
 
 @pytest.mark.gpu
