@@ -149,7 +149,7 @@ def cpu_reference_run(steps, warmup, budget_s=25.0, full_size=False):
         O.set_threads(cores)
     data = synth.stem4d_hash_numpy(CPU_SAMPLE_SHAPE, seed=2, counts=500.0)
     shape, how = CPU_SAMPLE_SHAPE, "same generator, reduced scan size"
-    if full_size and mem_available_gb() >= 60.0:
+    if full_size and mem_available_gb() >= 60.0 and os.environ.get("CYTVDN_BENCH_CPU_FULL", "1") != "0":
         # the full 256x256x128x128 array: the sample block repeated over the scan axes (generating 1.07 G voxels
         # with the NumPy mirror of the device generator would take minutes; per-voxel cost does not depend on it)
         reps = (SHAPE_1GPU[0] // shape[0], SHAPE_1GPU[1] // shape[1], 1, 1)
