@@ -311,7 +311,8 @@ int cytvdn_stream_plan_sharded(const cytvdn_denoise_params *params, int64_t budg
  *   create -> export -> [exchange the 128-byte handles] -> connect(0, lower's handle), connect(1, upper's handle)
  *   -> load(block) -> iterate(nF, nU) [-> iterate ...] -> sums / store -> [all ranks synchronised] -> disconnect ->
  *   [barrier] -> destroy.
- * All ranks must enqueue the same iterations.  A shard may be re-loaded and re-run any number of times; all ranks
+ * All ranks must enqueue the same iterations.  A shard is driven by one host thread at a time (different shards may be
+ * driven from different threads).  A shard may be re-loaded and re-run any number of times; all ranks
  * must have finished (cytvdn_shard_synchronize + a barrier of the caller's) before any of them is destroyed.
  * ---------------------------------------------------------------------------------------------------------------
  */
