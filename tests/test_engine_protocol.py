@@ -170,7 +170,7 @@ def test_engine_protocol_model_has_teeth():
     for old, new, args in (
             ("all(R.whole[side] >= it or R.box[side][b] >= it for b in nb)",
              "all(R.whole[side] >= it or R.box[side][b] >= it for b in ([nb[len(nb) // 2]] if len(nb) == 3 else nb))", (3, 4, 9, True)),
-            ("if it > 0:                                  # counters", "if False:", (2, 1, 7, False))):
+            ("if it > 0:                                  # counters", "if False:                                   # counters", (2, 1, 7, False))):
         assert old in src
         ns = {"__file__": __file__}
         exec(compile(src.replace(old, new), "mutated_model", "exec"), ns)
