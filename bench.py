@@ -444,6 +444,9 @@ def main():
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the parity checks over the process group")
     ap.add_argument("--no-alone", action="store_true", help="N > 1: skip the single-GPU run of one shard's shape")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling point of config 5 itself")
+    ap.add_argument("--extras-timeout", type=float, default=120.0,
+                    help="N > 1: seconds the side measurements (e2e, single shard, strong scaling, CPU baseline) may take "
+                         "before the line is emitted without the unfinished ones")
     ap.add_argument("--timeline", default=None, help="N > 1: write per-phase CUDA-event timings of the timed steps here")
     ap.add_argument("--timeline-full", action="store_true", help="keep every iteration of every rank in the timeline file")
     args = ap.parse_args()

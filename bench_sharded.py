@@ -273,6 +273,41 @@ def run_sharded(args):
                                    "hence frac can exceed 1; see `moved`")
             roofline["moved"] = {"bytes_per_voxel": 76, "GB/s": moved, "frac": moved / peak}
 
+        # ---- the headline measurement is complete.  What follows (end to end, the single-shard figure, the strong
+        #      scaling point, the CPU baseline) are side measurements: a safety net makes sure the line is printed even
+        #      if one of them should hang (a timer shorter than NCCL's timeout emits what is finished and ends the run).
+        check.update({"bnorm_last": float(last[0]), "delta_last": float(last[1] / last[2]) if last[2] else None})
+        extras = {"e2e": None, "alone": None, "strong": None, "cpu": None}
+
+        def emit():
+            if rank != 0:
+                return
+            line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": dict(workload_config(world) if not args.shape else
+                                   {"workload": f"4-D FISTA fp32 sharded, {'x'.join(map(str, per))} per GPU (non-default)"},
+                                   schedule=schedule),
+                    "roofline": roofline, "cpu_baseline": extras["cpu"], "e2e": extras["e2e"], "gpu_launches": int(launches[0]),
+                    "clocks": clk, "check": check, "single_gpu_same_shard": extras["alone"], "timeline": timeline,
+                    "strong_scaling_config5": extras["strong"]}
+            print(json.dumps(line), flush=True)
+
+        import threading
+
+        def emergency():
+            for k in extras:
+                if extras[k] is None:
+                    extras[k] = {"value": None, "error": f"side measurement not finished after {args.extras_timeout} s; "
+                                                          "the line was emitted by the safety net"}
+            try:
+                emit()
+            finally:
+                os._exit(0)
+        net = threading.Timer(args.extras_timeout, emergency)
+        net.daemon = True
+        net.start()
+
         # ---- end to end: pinned host shard in, pinned host owned planes out, through the public sharded API ----
         e2e = None
         if not args.no_e2e:
@@ -337,6 +372,7 @@ def run_sharded(args):
                 del host_in, host_out
             except Exception as e:          # e.g. not enough pinned host memory on this box
                 e2e = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
+        extras["e2e"] = e2e
 
         # ---- like-for-like single-GPU figure: one shard of the same stored shape alone on rank 0 -------------
         alone = None
@@ -366,6 +402,7 @@ def run_sharded(args):
                                  "neighbours: ms_per_step of the N-GPU run / this = per-GPU efficiency like for like"}
                 alone["efficiency_like_for_like"] = ms1 / ms_per_step
             dist.barrier()
+        extras["alone"] = alone
 
         # ---- strong scaling of BASELINE config 5 itself (the fixed 1024x1024x128x128 array, 69 GB raw) ------------
         # 8 GPUs: the main line above IS config 5 (fused, 19 arrays = 166 GB per GPU).  4 GPUs: 258 planes per GPU do not
@@ -428,22 +465,12 @@ def run_sharded(args):
                                  f"page-locked host memory between passes: 550 GB + 137 GB for data and result; this box has "
                                  f"{mem_available_gb():.0f} GB.  tools/sharded_stream_bench.py runs that schedule at the largest "
                                  "size the host holds (profiles/r2_sharded_stream_bench.jsonl)."}
-        cpu = None
+        extras["strong"] = strong
         if rank == 0 and not args.no_cpu:
             r_ = cpu_reference_run(5, 1, budget_s=15.0)
-            cpu = {"value": r_["value"], "unit": UNIT, "cores": r_["cores"], "kind": r_["kind"], "sample": r_["sample"]}
-        if rank == 0:
-            check.update({"bnorm_last": float(last[0]), "delta_last": float(last[1] / last[2]) if last[2] else None})
-            line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                    "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                    "config": dict(workload_config(world) if not args.shape else
-                                   {"workload": f"4-D FISTA fp32 sharded, {'x'.join(map(str, per))} per GPU (non-default)"},
-                                   schedule=schedule),
-                    "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches[0]),
-                    "clocks": clk, "check": check, "single_gpu_same_shard": alone, "timeline": timeline,
-                    "strong_scaling_config5": strong}
-            print(json.dumps(line), flush=True)
+            extras["cpu"] = {"value": r_["value"], "unit": UNIT, "cores": r_["cores"], "kind": r_["kind"], "sample": r_["sample"]}
+        net.cancel()
+        emit()
     except BaseException:
         # a failing rank leaves at once (no collective tear-down the others might not join); torchrun then stops the rest
         import traceback
