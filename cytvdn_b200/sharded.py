@@ -1,14 +1,26 @@
-"""Scan-axis sharding of the 4-D TV iteration over several GPUs (one process per GPU).
+"""Scan-axis sharding of the 4-D TV iteration over several GPUs.
 
-Re-expression of the reference's MPI scheme (`cyTVDN/mpi.py:130-210` partition, `:314-438`
-iteration + exchange; description `README.md:104-120`) with torch.distributed / NCCL:
+Re-expression of the reference's MPI scheme (`cyTVDN/mpi.py:130-210` partition, `:314-438` iteration + exchange;
+description `README.md:104-120`):
 
-* tiles over the scan axes 0/1 on a ``wx x wy`` grid, each tile stores its owned block plus ONE
-  overlap plane towards every existing neighbour (`mpi.py:165-196`);
-* every rank runs the same two fused kernels on its local block;
-* after half-step A the accumulator of a split axis is shifted right: the sender's LAST OWNED
-  plane replaces the receiver's plane 0; after half-step B the reconstruction is shifted left:
-  the sender's FIRST OWNED plane replaces the receiver's last plane.
+* tiles over the scan axes 0/1 on a ``wx x wy`` grid, each tile stores its owned block plus ONE overlap plane towards
+  every existing neighbour (`mpi.py:165-196`);
+* every rank runs the same kernels on its local block;
+* the planes that travel are the sender's first / last OWNED planes (corrected indices).
+
+Two implementations share ``ShardPlan``:
+
+**The C-ABI shard engine** (``EngineShard``, ``denoise4D_engine``; `csrc/cytvdn_shard.cu`, round 2) -- the default for
+1-D splits of scan axis 0.  The loop lives in the library: fused single-pass sweeps, halo planes first, the COPY ENGINES
+push the new first / last owned recon plane into the neighbours' overlap planes through peer pointers (CUDA IPC between
+processes) under the interior sweep, a counter in the neighbour's header announces each plane.  torch.distributed only
+carries the 128-byte handles and one all-reduce of three doubles per iteration.  Host arrays in and out are pipelined
+box by box along scan axis 1 (``cytvdn_shard_run_host``).  From one process: ``tv.denoise4D(..., devices=[0, 1, ...])``.
+
+**The torch.distributed / NCCL schedules of round 1** (``CudaShard``, ``denoise4D_sharded``, ``denoise4D_peer``) -- kept
+for the reference's 2-D ``(wx, wy)`` grids (``grid="mpi"``, strided halo planes), for the reference-structured two-pass
+iteration (two exchanges per iteration: accumulators right, reconstruction left) and as the cross-check of the engine
+(`bench_sharded.py` compares all of them on every multi-GPU run).
 
 Deviations from `mpi.py`, all required for the sharded result to equal the single-process one
 (verified there against the compiled reference):
@@ -21,15 +33,8 @@ Deviations from `mpi.py`, all required for the sharded result to equal the singl
   - ``b_norm`` / ``delta`` are produced: sums over OWNED voxels, all-reduced (3 doubles / iteration).
 `mpi.py:84` knows ``BC_mode=2`` only; here ``ShardPlan(..., periodic=True)`` adds ``BC_mode=0``: the first and the last
 tile of a split axis exchange planes too and the kernels treat that axis as Jia-Zhao inside the block
-(``cytvdn_step_opts.flags`` bits 8..11), so the wrap is done by the exchange.
-
-Default layout on NVSwitch: 1-D over axis 0 (contiguous halo planes, two neighbours); the halo planes
-are computed first, exchanged right away on the compute stream (a 67 MB plane takes ~0.3 ms of a ~28 ms
-iteration and the neighbours' halo planes are ready at the same moment), then the interior is swept.
-Running the exchange on a side stream under the interior sweep (``CYTVDN_SHARD_EXCHANGE=overlap``) was
-measured slower on B200: NCCL's send/recv CTAs displace CTAs of the persistent sweep.  The reference's 2-D
-``(wx, wy)`` heuristic (`mpi.py:131-150`) is available as ``grid="mpi"`` (no overlap of compute and
-exchange in that mode).
+(``cytvdn_step_opts.flags`` bits 8..11), so the wrap is done by the exchange; the engine also knows the clamped mirror
+(``periodic=2``, ``BC_mode=3``).
 """
 from __future__ import annotations
 
