@@ -332,7 +332,8 @@ def run_single(args):
         roofline = {"bound": "hbm",
                     "kernel": "tv_fused_kernel<float,4,FISTA,4D> (whole iteration = half-steps A+B in one pass)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic.get("tv_fused_kernel"), "peak_source": peak_src, "ms_per_launch": a_ms,
+                    "traffic": traffic.get("tv_fused_kernel"), "traffic_source": traffic.get("_source"),
+                    "peak_source": peak_src, "ms_per_launch": a_ms,
                     "bytes_per_voxel": BYTES_A + BYTES_B,
                     "variant": "fused single pass: the contract's 96 B/voxel of work (SURVEY 8d) is done while moving "
                                "76 B/voxel (every array crosses HBM once), hence frac > 1; see `moved`",
